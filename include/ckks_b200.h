@@ -1,0 +1,157 @@
+/*
+ * ckks_b200.h -- C ABI of the B200-native CKKS evaluation engine (libckks_b200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path: the Microsoft SEAL
+ * `Evaluator` surface that MarwanNour/SEAL-FYP-Logistic-Regression calls from its matrix /
+ * vector helpers and its logistic-regression loop.  The reference reaches SEAL through
+ * `#include "seal/seal.h"` (helper.h:4) and `target_link_libraries(<exe> SEAL::seal)`
+ * (CMakeLists.txt:25-40); the C++ shim in
+ * seal-fyp-logistic-regression_b200/include/seal/seal.h forwards every Evaluator member to
+ * one of the entry points below.  Each entry point names the SEAL member it stands in for
+ * and a reference call site.
+ *
+ * Conventions
+ *   - plain C: opaque handles, raw device/host pointers, sizes, int status codes
+ *     (0 = CKKS_OK); no C++ or torch types.  ckks_last_error() gives the message.
+ *   - all polynomial data are uint64 words in device memory, always in NTT form
+ *     (bit-reversed evaluation order) exactly as SEAL stores CKKS data.
+ *   - a ckks_view describes a batch of ciphertexts (or plaintexts, size == 1):
+ *       word address of (b, poly s, limb j, coeff c)
+ *           = data + b*batch_stride + s*poly_stride + j*N + c
+ *     limb j is modulo prime j of the context; the special prime is prime K-1.
+ *     Keeping poly_stride fixed at the top level's L*N makes mod-switch a metadata change.
+ *   - every call is asynchronous on the given CUDA stream (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream) and never synchronises the device.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef CKKS_B200_H
+#define CKKS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CKKS_OK 0
+#define CKKS_ERR_INVALID 1   /* std::invalid_argument in SEAL */
+#define CKKS_ERR_CUDA 2
+#define CKKS_ERR_NOMEM 3
+#define CKKS_ERR_LOGIC 4     /* std::logic_error in SEAL */
+
+typedef struct ckks_ctx ckks_ctx;
+typedef struct ckks_keyset ckks_keyset;
+typedef void *ckks_stream;
+
+typedef struct ckks_view {
+    uint64_t *data;        /* device pointer */
+    uint64_t batch_stride; /* words between consecutive ciphertexts */
+    uint64_t poly_stride;  /* words between consecutive polynomials */
+    int32_t batch;         /* number of ciphertexts */
+    int32_t size;          /* polynomials per ciphertext (1 for a plaintext) */
+    int32_t limbs;         /* active RNS limbs L (primes 0..L-1) */
+    int32_t reserved;
+} ckks_view;
+
+const char *ckks_last_error(void);
+const char *ckks_version(void);
+
+/* ---- context: SEAL EncryptionParameters + SEALContext (logistic_regression_ckks.cpp:418-427,
+ * linear_transformation2.cpp:229-239).  primes[K-1] is the special prime. */
+int ckks_ctx_create(int log_n, int n_primes, const uint64_t *primes, int device, ckks_ctx **out);
+void ckks_ctx_destroy(ckks_ctx *ctx);
+int ckks_ctx_log_n(const ckks_ctx *ctx);
+int ckks_ctx_n_primes(const ckks_ctx *ctx);
+uint64_t ckks_ctx_prime(const ckks_ctx *ctx, int j);
+/* 1 = divide-and-round (SEAL 3.4.5), 0 = floor; see SURVEY.md A.7/A.8 */
+int ckks_ctx_set_rounding(ckks_ctx *ctx, int round_half);
+/* cap (bytes) on the internal key-switch workspace; larger batches are processed in chunks */
+int ckks_ctx_set_workspace_cap(ckks_ctx *ctx, size_t bytes);
+/* pre-allocate the workspace for key switching `batch` ciphertexts at `limbs` (needed before
+ * CUDA-graph capture, which forbids allocation) */
+int ckks_ctx_reserve(ckks_ctx *ctx, int batch, int limbs);
+/* number of kernels this context has launched since creation / since the last reset */
+uint64_t ckks_ctx_launch_count(const ckks_ctx *ctx);
+void ckks_ctx_reset_launch_count(ckks_ctx *ctx);
+
+/* ---- memory / stream helpers for hosts that do not bring their own allocator */
+int ckks_dev_alloc(ckks_ctx *ctx, size_t bytes, void **out);
+int ckks_dev_free(ckks_ctx *ctx, void *p);
+int ckks_host_alloc(size_t bytes, void **out);   /* pinned */
+int ckks_host_free(void *p);
+int ckks_upload(ckks_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, ckks_stream s);
+int ckks_download(ckks_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, ckks_stream s);
+int ckks_stream_sync(ckks_ctx *ctx, ckks_stream s);
+
+/* ---- negacyclic NTT (SEAL util::ntt_negacyclic_harvey / inverse_...): n_polys x limbs limbs in
+ * place, limb l uses prime first_prime + l; canonical output in [0,p). */
+int ckks_ntt_forward(ckks_ctx *ctx, uint64_t *data, int n_polys, int limbs, int first_prime,
+                     uint64_t poly_stride, ckks_stream s);
+int ckks_ntt_inverse(ckks_ctx *ctx, uint64_t *data, int n_polys, int limbs, int first_prime,
+                     uint64_t poly_stride, ckks_stream s);
+
+/* ---- element-wise evaluator ops (out may alias an input when strides are identical) */
+/* Evaluator::add / add_inplace (helper.h:247,484; logistic_regression_ckks.cpp:131) */
+int ckks_add(ckks_ctx *ctx, const ckks_view *a, const ckks_view *b, const ckks_view *out, ckks_stream s);
+/* Evaluator::sub (logistic_regression_ckks.cpp:288,341) */
+int ckks_sub(ckks_ctx *ctx, const ckks_view *a, const ckks_view *b, const ckks_view *out, ckks_stream s);
+/* Evaluator::negate_inplace (logistic_regression_ckks.cpp:342) */
+int ckks_negate(ckks_ctx *ctx, const ckks_view *a, const ckks_view *out, ckks_stream s);
+/* Evaluator::multiply / multiply_inplace, sizes (Sa,Sb) -> Sa+Sb-1 (helper.h:222,432;
+ * matrix_multiplication.cpp:105,126; logistic_regression_ckks.cpp:184) */
+int ckks_multiply(ckks_ctx *ctx, const ckks_view *a, const ckks_view *b, const ckks_view *out, ckks_stream s);
+/* Evaluator::multiply_plain (helper.h:250,256,271).  pt->size == 1; pt->batch is 1 (broadcast)
+ * or ct->batch */
+int ckks_multiply_plain(ckks_ctx *ctx, const ckks_view *ct, const ckks_view *pt, const ckks_view *out,
+                        ckks_stream s);
+/* Evaluator::add_plain_inplace (logistic_regression_ckks.cpp:198) */
+int ckks_add_plain(ckks_ctx *ctx, const ckks_view *ct, const ckks_view *pt, const ckks_view *out,
+                   ckks_stream s);
+/* Evaluator::add_many (helper.h:233,259,276,320): out (batch 1) = sum over the batch of `in`;
+ * also the mod-q add that combines all-gathered partial ciphertexts across GPUs */
+int ckks_add_many(ckks_ctx *ctx, const ckks_view *in, const ckks_view *out, ckks_stream s);
+/* SEAL's "result ciphertext is transparent" test: *flag_dev (device int32, one per batch entry)
+ * is set to 1 when polys 1.. of the entry are all zero */
+int ckks_is_transparent(ckks_ctx *ctx, const ckks_view *ct, int32_t *flag_dev, ckks_stream s);
+
+/* ---- key switching.  Key layout (device): [digit i < K-1][component k < 2][limb j < K][N],
+ * NTT form at the key level, as produced by SEAL KeyGenerator::generate_one_kswitch_key. */
+size_t ckks_ksk_words(const ckks_ctx *ctx);
+/* Evaluator::relinearize_inplace for size 3 -> 2 (helper.h:440,541;
+ * logistic_regression_ckks.cpp:187).  out may alias in. */
+int ckks_relinearize(ckks_ctx *ctx, const ckks_view *in, const uint64_t *rlk, const ckks_view *out,
+                     ckks_stream s);
+/* Evaluator::apply_galois: one Galois step of rotate_vector (permutation + key switch).
+ * out must not alias in. */
+int ckks_apply_galois(ckks_ctx *ctx, const ckks_view *in, uint64_t galois_elt, const uint64_t *gk,
+                      const ckks_view *out, ckks_stream s);
+/* util::steps_to_galois_elt; returns 0 for |steps| >= N/2 ("step count too large") */
+uint64_t ckks_galois_elt_from_step(const ckks_ctx *ctx, int steps);
+
+/* key registry = SEAL RelinKeys + GaloisKeys (device pointers are borrowed, not copied) */
+int ckks_keyset_create(ckks_ctx *ctx, ckks_keyset **out);
+void ckks_keyset_destroy(ckks_keyset *ks);
+int ckks_keyset_set_relin(ckks_keyset *ks, const uint64_t *rlk);
+int ckks_keyset_set_galois(ckks_keyset *ks, uint64_t galois_elt, const uint64_t *gk);
+int ckks_keyset_has_galois(const ckks_keyset *ks, uint64_t galois_elt);
+/* Evaluator::rotate_vector (helper.h:222,244,255,318,350,471,475) including SEAL's NAF fallback
+ * when the key for `steps` itself is absent.  out must not alias in.  `scratch` is a view like
+ * `out` (distinct storage) used to ping-pong composite rotations; may be NULL when the step
+ * maps to a single key. */
+int ckks_rotate(ckks_ctx *ctx, const ckks_keyset *ks, const ckks_view *in, int steps, const ckks_view *out,
+                const ckks_view *scratch, ckks_stream s);
+
+/* ---- rescale / mod switch */
+/* Evaluator::rescale_to_next_inplace (helper.h:441,543; matrix_multiplication.cpp:71-72):
+ * out->limbs == in->limbs - 1.  out may alias in when strides are identical. */
+int ckks_rescale(ckks_ctx *ctx, const ckks_view *in, const ckks_view *out, ckks_stream s);
+/* Evaluator::mod_switch_to_next_inplace on ciphertexts / NTT-form plaintexts
+ * (logistic_regression_ckks.cpp:177-182,227,286,295): copies limbs 0..out->limbs-1.  When in and
+ * out share storage and strides this is a no-op (the caller only lowers `limbs`). */
+int ckks_mod_switch_drop(ckks_ctx *ctx, const ckks_view *in, const ckks_view *out, ckks_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,565 @@
+// engine.cu -- context, launch logic and the extern "C" surface declared in include/ckks_b200.h.
+//
+// One context = one CKKS parameter set on one device.  Every entry point validates its views,
+// enqueues kernels on the caller's stream and returns; nothing here synchronises the device
+// and nothing falls back to the CPU.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ckks_b200.h"
+#include "kernels.cuh"
+#include "tables.h"
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(CKKS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));  \
+    } while (0)
+#define LAUNCH_CHECK(ctx)                                                                  \
+    do {                                                                                   \
+        (ctx)->launches++;                                                                 \
+        cudaError_t e__ = cudaPeekAtLastError();                                           \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(CKKS_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ context
+struct ckks_ctx {
+    int log_n = 0, n = 0, K = 0, device = 0;
+    std::vector<uint64_t> primes;
+    Tables t{};
+    void *d_mod = nullptr, *d_twf = nullptr, *d_twi = nullptr, *d_inv = nullptr, *d_invs = nullptr, *d_half = nullptr;
+    std::unordered_map<uint64_t, uint32_t *> perms;
+    u64 *ws = nullptr;
+    size_t ws_bytes = 0;
+    size_t ws_cap = size_t(1) << 30;
+    uint64_t launches = 0;
+};
+
+struct ckks_keyset {
+    ckks_ctx *ctx;
+    const uint64_t *relin = nullptr;
+    std::unordered_map<uint64_t, const uint64_t *> galois;
+};
+
+static int upload_vec(void **dst, const void *src, size_t bytes) {
+    CU(cudaMalloc(dst, bytes));
+    CU(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return CKKS_OK;
+}
+
+extern "C" const char *ckks_last_error(void) { return g_err.c_str(); }
+extern "C" const char *ckks_version(void) { return "ckks_b200 0.1 (sm_100a)"; }
+
+extern "C" int ckks_ctx_create(int log_n, int n_primes, const uint64_t *primes, int device, ckks_ctx **out) {
+    if (!out || !primes) return fail(CKKS_ERR_INVALID, "null argument");
+    if (log_n < 12 || log_n > 15) return fail(CKKS_ERR_INVALID, "poly_modulus_degree must be 4096..32768");
+    if (n_primes < 2 || n_primes > 32) return fail(CKKS_ERR_INVALID, "coeff_modulus needs 2..32 primes");
+    ckks::HostTables ht;
+    std::vector<uint64_t> pv(primes, primes + n_primes);
+    try {
+        ckks::build_tables(log_n, pv, ht);
+    } catch (const std::exception &e) {
+        return fail(CKKS_ERR_INVALID, e.what());
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(CKKS_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    CU(cudaSetDevice(device));
+    ckks_ctx *c = new ckks_ctx;
+    c->log_n = log_n;
+    c->n = 1 << log_n;
+    c->K = n_primes;
+    c->device = device;
+    c->primes = pv;
+    int rc;
+    if ((rc = upload_vec(&c->d_mod, ht.mod.data(), ht.mod.size() * 8)) ||
+        (rc = upload_vec(&c->d_twf, ht.twf.data(), ht.twf.size() * 8)) ||
+        (rc = upload_vec(&c->d_twi, ht.twi.data(), ht.twi.size() * 8)) ||
+        (rc = upload_vec(&c->d_inv, ht.inv.data(), ht.inv.size() * 8)) ||
+        (rc = upload_vec(&c->d_invs, ht.invs.data(), ht.invs.size() * 8)) ||
+        (rc = upload_vec(&c->d_half, ht.halfmod.data(), ht.halfmod.size() * 8))) {
+        ckks_ctx_destroy(c);
+        return rc;
+    }
+    c->t.mod = (const ModConst *)c->d_mod;
+    c->t.twf = (const tw_t *)c->d_twf;
+    c->t.twi = (const tw_t *)c->d_twi;
+    c->t.inv = (const u64 *)c->d_inv;
+    c->t.invs = (const u64 *)c->d_invs;
+    c->t.halfmod = (const u64 *)c->d_half;
+    c->t.K = n_primes;
+    c->t.round_half = 1;
+    *out = c;
+    return CKKS_OK;
+}
+
+extern "C" void ckks_ctx_destroy(ckks_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto &kv : c->perms) cudaFree(kv.second);
+    cudaFree(c->d_mod); cudaFree(c->d_twf); cudaFree(c->d_twi);
+    cudaFree(c->d_inv); cudaFree(c->d_invs); cudaFree(c->d_half);
+    cudaFree(c->ws);
+    delete c;
+}
+
+extern "C" int ckks_ctx_log_n(const ckks_ctx *c) { return c->log_n; }
+extern "C" int ckks_ctx_n_primes(const ckks_ctx *c) { return c->K; }
+extern "C" uint64_t ckks_ctx_prime(const ckks_ctx *c, int j) { return (j >= 0 && j < c->K) ? c->primes[j] : 0; }
+extern "C" int ckks_ctx_set_rounding(ckks_ctx *c, int r) {
+    c->t.round_half = r ? 1 : 0;
+    return CKKS_OK;
+}
+extern "C" int ckks_ctx_set_workspace_cap(ckks_ctx *c, size_t bytes) {
+    c->ws_cap = bytes;
+    return CKKS_OK;
+}
+extern "C" uint64_t ckks_ctx_launch_count(const ckks_ctx *c) { return c->launches; }
+extern "C" void ckks_ctx_reset_launch_count(ckks_ctx *c) { c->launches = 0; }
+
+static int ensure_ws(ckks_ctx *c, size_t bytes) {
+    if (bytes <= c->ws_bytes) return CKKS_OK;
+    CU(cudaSetDevice(c->device));
+    if (c->ws) {
+        CU(cudaDeviceSynchronize());  // growing mid-stream: let in-flight users of the old buffer finish
+        CU(cudaFree(c->ws));
+        c->ws = nullptr;
+        c->ws_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc((void **)&c->ws, bytes);
+    if (e != cudaSuccess) return fail(CKKS_ERR_NOMEM, "workspace allocation failed");
+    c->ws_bytes = bytes;
+    return CKKS_OK;
+}
+
+// words of workspace one key switch needs per ciphertext at L limbs
+static size_t ks_words_per_ct(const ckks_ctx *c, int L) {
+    return (size_t)c->n * ((size_t)L + (size_t)L * (L + 1) + 2 * (size_t)(L + 1) + 2 * (size_t)L);
+}
+static int ks_chunk(const ckks_ctx *c, int B, int L) {
+    size_t per = ks_words_per_ct(c, L) * 8;
+    size_t fit = c->ws_cap / per;
+    if (fit < 1) fit = 1;
+    if (fit > 16384) fit = 16384;
+    return (int)(fit < (size_t)B ? fit : (size_t)B);
+}
+
+extern "C" int ckks_ctx_reserve(ckks_ctx *c, int batch, int limbs) {
+    if (batch < 1 || limbs < 1 || limbs >= c->K + 1) return fail(CKKS_ERR_INVALID, "bad reserve request");
+    int bc = ks_chunk(c, batch, limbs);
+    return ensure_ws(c, ks_words_per_ct(c, limbs) * 8 * (size_t)bc);
+}
+
+// ------------------------------------------------------------------------------------ helpers
+extern "C" int ckks_dev_alloc(ckks_ctx *c, size_t bytes, void **out) {
+    CU(cudaSetDevice(c->device));
+    if (cudaMalloc(out, bytes) != cudaSuccess) return fail(CKKS_ERR_NOMEM, "device allocation failed");
+    return CKKS_OK;
+}
+extern "C" int ckks_dev_free(ckks_ctx *c, void *p) {
+    CU(cudaSetDevice(c->device));
+    CU(cudaFree(p));
+    return CKKS_OK;
+}
+extern "C" int ckks_host_alloc(size_t bytes, void **out) {
+    if (cudaMallocHost(out, bytes) != cudaSuccess) return fail(CKKS_ERR_NOMEM, "pinned allocation failed");
+    return CKKS_OK;
+}
+extern "C" int ckks_host_free(void *p) {
+    CU(cudaFreeHost(p));
+    return CKKS_OK;
+}
+extern "C" int ckks_upload(ckks_ctx *, void *dst, const void *src, size_t bytes, ckks_stream s) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)s));
+    return CKKS_OK;
+}
+extern "C" int ckks_download(ckks_ctx *, void *dst, const void *src, size_t bytes, ckks_stream s) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+    return CKKS_OK;
+}
+extern "C" int ckks_stream_sync(ckks_ctx *, ckks_stream s) {
+    CU(cudaStreamSynchronize((cudaStream_t)s));
+    return CKKS_OK;
+}
+
+static inline DView dv(const ckks_view *v) { return DView{(u64 *)v->data, v->batch_stride, v->poly_stride}; }
+
+static int check_view(const ckks_ctx *c, const ckks_view *v, const char *name) {
+    if (!v || !v->data) return fail(CKKS_ERR_INVALID, std::string(name) + ": null view");
+    if (v->batch < 1 || v->size < 1) return fail(CKKS_ERR_INVALID, std::string(name) + ": empty view");
+    if (v->limbs < 1 || v->limbs > c->K - 1)
+        return fail(CKKS_ERR_INVALID, std::string(name) + ": limbs outside the data levels of this context");
+    if ((size_t)v->poly_stride < (size_t)v->limbs * c->n) return fail(CKKS_ERR_INVALID, std::string(name) + ": poly_stride too small");
+    if (v->batch > 1 && (size_t)v->batch_stride < (size_t)v->size * v->poly_stride && v->batch_stride != 0)
+        return fail(CKKS_ERR_INVALID, std::string(name) + ": batch_stride too small");
+    if (((uintptr_t)v->data & 15) || (v->poly_stride & 1) || (v->batch_stride & 1))
+        return fail(CKKS_ERR_INVALID, std::string(name) + ": data must be 16-byte aligned");
+    if (v->batch > 65535) return fail(CKKS_ERR_INVALID, std::string(name) + ": batch > 65535");
+    return CKKS_OK;
+}
+static int same_shape(const ckks_view *a, const ckks_view *b, const char *what) {
+    if (a->batch != b->batch || a->size != b->size || a->limbs != b->limbs)
+        return fail(CKKS_ERR_INVALID, std::string(what) + " parameter mismatch");
+    return CKKS_OK;
+}
+
+#define DISPATCH_LOGN(c, MACRO)                                                   \
+    switch ((c)->log_n) {                                                         \
+    case 12: MACRO(12); break;                                                    \
+    case 13: MACRO(13); break;                                                    \
+    case 14: MACRO(14); break;                                                    \
+    case 15: MACRO(15); break;                                                    \
+    default: return fail(CKKS_ERR_INVALID, "unsupported degree");                 \
+    }
+
+// ------------------------------------------------------------------------------------ NTT API
+static int ntt_api(ckks_ctx *c, uint64_t *data, int n_polys, int limbs, int first_prime, uint64_t ps, bool inverse, cudaStream_t st) {
+    if (!data || n_polys < 1 || limbs < 1 || first_prime < 0 || first_prime + limbs > c->K)
+        return fail(CKKS_ERR_INVALID, "ntt: bad arguments");
+    if (ps < (uint64_t)limbs * c->n) return fail(CKKS_ERR_INVALID, "ntt: poly_stride too small");
+    if (n_polys > 65535) return fail(CKKS_ERR_INVALID, "ntt: more than 65535 polys");
+    CU(cudaSetDevice(c->device));
+    DView v{(u64 *)data, ps, 0};
+#define RUN(LN)                                                                                             \
+    {                                                                                                       \
+        dim3 gc(NttGeo<LN>::COL_TILES, limbs, n_polys), gr(NttGeo<LN>::ROW_TILES, limbs, n_polys);          \
+        if (!inverse) {                                                                                     \
+            k_fwd_col<LN><<<gc, NTT_THREADS, 0, st>>>(v, v, limbs, first_prime, c->t); LAUNCH_CHECK(c);     \
+            k_fwd_row<LN><<<gr, NTT_THREADS, 0, st>>>(v, v, limbs, first_prime, c->t); LAUNCH_CHECK(c);     \
+        } else {                                                                                            \
+            k_inv_row<LN><<<gr, NTT_THREADS, 0, st>>>(v, v, limbs, first_prime, c->t); LAUNCH_CHECK(c);     \
+            k_inv_col<LN, false><<<gc, NTT_THREADS, 0, st>>>(v, v, limbs, first_prime, c->t); LAUNCH_CHECK(c); \
+        }                                                                                                   \
+    }
+    DISPATCH_LOGN(c, RUN)
+#undef RUN
+    return CKKS_OK;
+}
+extern "C" int ckks_ntt_forward(ckks_ctx *c, uint64_t *d, int np, int l, int fp, uint64_t ps, ckks_stream s) {
+    return ntt_api(c, d, np, l, fp, ps, false, (cudaStream_t)s);
+}
+extern "C" int ckks_ntt_inverse(ckks_ctx *c, uint64_t *d, int np, int l, int fp, uint64_t ps, ckks_stream s) {
+    return ntt_api(c, d, np, l, fp, ps, true, (cudaStream_t)s);
+}
+
+// ------------------------------------------------------------------------------------ element-wise
+static inline dim3 ew_grid(const ckks_ctx *c, int y, int z) { return dim3((c->n / 2 + 255) / 256, y, z); }
+
+static int addsub(ckks_ctx *c, int op, const ckks_view *a, const ckks_view *b, const ckks_view *o, cudaStream_t st) {
+    int rc;
+    if ((rc = check_view(c, a, "a")) || (rc = check_view(c, o, "out")) || (rc = same_shape(a, o, "destination"))) return rc;
+    if (op != 2 && ((rc = check_view(c, b, "b")) || (rc = same_shape(a, b, "encrypted1 and encrypted2")))) return rc;
+    CU(cudaSetDevice(c->device));
+    dim3 g = ew_grid(c, a->size * a->limbs, a->batch);
+    DView vb = op != 2 ? dv(b) : dv(a);
+    if (op == 0) k_ew_addsub<0><<<g, 256, 0, st>>>(dv(a), vb, dv(o), a->limbs, c->n, c->t);
+    if (op == 1) k_ew_addsub<1><<<g, 256, 0, st>>>(dv(a), vb, dv(o), a->limbs, c->n, c->t);
+    if (op == 2) k_ew_addsub<2><<<g, 256, 0, st>>>(dv(a), vb, dv(o), a->limbs, c->n, c->t);
+    LAUNCH_CHECK(c);
+    return CKKS_OK;
+}
+extern "C" int ckks_add(ckks_ctx *c, const ckks_view *a, const ckks_view *b, const ckks_view *o, ckks_stream s) {
+    return addsub(c, 0, a, b, o, (cudaStream_t)s);
+}
+extern "C" int ckks_sub(ckks_ctx *c, const ckks_view *a, const ckks_view *b, const ckks_view *o, ckks_stream s) {
+    return addsub(c, 1, a, b, o, (cudaStream_t)s);
+}
+extern "C" int ckks_negate(ckks_ctx *c, const ckks_view *a, const ckks_view *o, ckks_stream s) {
+    return addsub(c, 2, a, nullptr, o, (cudaStream_t)s);
+}
+
+extern "C" int ckks_multiply(ckks_ctx *c, const ckks_view *a, const ckks_view *b, const ckks_view *o, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, a, "a")) || (rc = check_view(c, b, "b")) || (rc = check_view(c, o, "out"))) return rc;
+    if (a->batch != b->batch || a->limbs != b->limbs) return fail(CKKS_ERR_INVALID, "encrypted1 and encrypted2 parameter mismatch");
+    if (o->batch != a->batch || o->limbs != a->limbs || o->size != a->size + b->size - 1)
+        return fail(CKKS_ERR_INVALID, "destination parameter mismatch");
+    if (o->data == a->data || o->data == b->data) return fail(CKKS_ERR_INVALID, "multiply: out must not alias an input");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)s;
+    dim3 g = ew_grid(c, a->limbs, a->batch);
+#define MUL(SA, SB) k_ew_multiply<SA, SB><<<g, 256, 0, st>>>(dv(a), dv(b), dv(o), a->limbs, c->n, c->t)
+    if (a->size == 2 && b->size == 2) MUL(2, 2);
+    else if (a->size == 3 && b->size == 2) MUL(3, 2);
+    else if (a->size == 2 && b->size == 3) MUL(2, 3);
+    else if (a->size == 3 && b->size == 3) MUL(3, 3);
+    else if (a->size == 2 && b->size == 1) MUL(2, 1);
+    else if (a->size == 1 && b->size == 2) MUL(1, 2);
+    else return fail(CKKS_ERR_INVALID, "multiply: ciphertext sizes above 3 are not supported");
+#undef MUL
+    LAUNCH_CHECK(c);
+    return CKKS_OK;
+}
+
+static int plain_op(ckks_ctx *c, bool mul, const ckks_view *ct, const ckks_view *pt, const ckks_view *o, cudaStream_t st) {
+    int rc;
+    if ((rc = check_view(c, ct, "encrypted")) || (rc = check_view(c, pt, "plain")) || (rc = check_view(c, o, "out")) ||
+        (rc = same_shape(ct, o, "destination")))
+        return rc;
+    if (pt->size != 1 || pt->limbs != ct->limbs || (pt->batch != 1 && pt->batch != ct->batch))
+        return fail(CKKS_ERR_INVALID, "encrypted and plain parameter mismatch");
+    CU(cudaSetDevice(c->device));
+    DView p = dv(pt);
+    if (pt->batch == 1) p.bs = 0;
+    dim3 g = ew_grid(c, ct->size * ct->limbs, ct->batch);
+    if (mul) k_ew_mul_plain<<<g, 256, 0, st>>>(dv(ct), p, dv(o), ct->limbs, c->n, c->t);
+    else k_ew_add_plain<<<g, 256, 0, st>>>(dv(ct), p, dv(o), ct->limbs, c->n, c->t);
+    LAUNCH_CHECK(c);
+    return CKKS_OK;
+}
+extern "C" int ckks_multiply_plain(ckks_ctx *c, const ckks_view *ct, const ckks_view *pt, const ckks_view *o, ckks_stream s) {
+    return plain_op(c, true, ct, pt, o, (cudaStream_t)s);
+}
+extern "C" int ckks_add_plain(ckks_ctx *c, const ckks_view *ct, const ckks_view *pt, const ckks_view *o, ckks_stream s) {
+    return plain_op(c, false, ct, pt, o, (cudaStream_t)s);
+}
+
+extern "C" int ckks_add_many(ckks_ctx *c, const ckks_view *in, const ckks_view *o, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, in, "in")) || (rc = check_view(c, o, "out"))) return rc;
+    if (o->batch != 1 || o->size != in->size || o->limbs != in->limbs) return fail(CKKS_ERR_INVALID, "destination parameter mismatch");
+    CU(cudaSetDevice(c->device));
+    k_ew_add_many<<<ew_grid(c, in->size * in->limbs, 1), 256, 0, (cudaStream_t)s>>>(dv(in), dv(o), in->batch, in->limbs, c->n, c->t);
+    LAUNCH_CHECK(c);
+    return CKKS_OK;
+}
+
+extern "C" int ckks_is_transparent(ckks_ctx *c, const ckks_view *ct, int32_t *flags, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, ct, "encrypted"))) return rc;
+    if (!flags) return fail(CKKS_ERR_INVALID, "null flags");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)s;
+    k_fill_i32<<<(ct->batch + 255) / 256, 256, 0, st>>>(flags, ct->batch, 1);
+    LAUNCH_CHECK(c);
+    if (ct->size > 1) {
+        k_transparent<<<ew_grid(c, (ct->size - 1) * ct->limbs, ct->batch), 256, 0, st>>>(dv(ct), flags, ct->limbs, c->n);
+        LAUNCH_CHECK(c);
+    }
+    return CKKS_OK;
+}
+
+extern "C" int ckks_mod_switch_drop(ckks_ctx *c, const ckks_view *in, const ckks_view *o, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, in, "in")) || (rc = check_view(c, o, "out"))) return rc;
+    if (o->batch != in->batch || o->size != in->size || o->limbs >= in->limbs)
+        return fail(CKKS_ERR_INVALID, "mod_switch: destination must sit lower in the modulus chain");
+    if (o->data == in->data) {
+        if (o->poly_stride == in->poly_stride && o->batch_stride == in->batch_stride) return CKKS_OK;  // metadata only
+        return fail(CKKS_ERR_INVALID, "mod_switch: in-place only with identical strides");
+    }
+    CU(cudaSetDevice(c->device));
+    k_ew_copy<<<ew_grid(c, o->size * o->limbs, o->batch), 256, 0, (cudaStream_t)s>>>(dv(in), dv(o), o->limbs, c->n);
+    LAUNCH_CHECK(c);
+    return CKKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ key switching
+extern "C" size_t ckks_ksk_words(const ckks_ctx *c) { return (size_t)(c->K - 1) * 2 * c->K * c->n; }
+extern "C" uint64_t ckks_galois_elt_from_step(const ckks_ctx *c, int steps) { return ckks::galois_elt_from_step(c->log_n, steps); }
+
+static int get_perm(ckks_ctx *c, uint64_t g, const uint32_t **out) {
+    if (!(g & 1) || g >= 2ull * c->n) return fail(CKKS_ERR_INVALID, "Galois element is not valid");
+    auto it = c->perms.find(g);
+    if (it == c->perms.end()) {
+        std::vector<uint32_t> h;
+        ckks::build_galois_perm(c->log_n, g, h);
+        uint32_t *d = nullptr;
+        CU(cudaSetDevice(c->device));
+        CU(cudaMalloc((void **)&d, h.size() * 4));
+        CU(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        it = c->perms.emplace(g, d).first;
+    }
+    *out = it->second;
+    return CKKS_OK;
+}
+
+// mode 1: relinearize (target = in poly 2, base = in polys 0,1)
+// mode 2: Galois      (target = permuted in poly 1, base = permuted in poly 0)
+static int keyswitch(ckks_ctx *c, int mode, const ckks_view *in, const uint32_t *perm, const uint64_t *ksk, const ckks_view *out, cudaStream_t st) {
+    const int L = in->limbs, B = in->batch, K = c->K;
+    const size_t N = c->n;
+    const int Bc = ks_chunk(c, B, L);
+    int rc;
+    if ((rc = ensure_ws(c, ks_words_per_ct(c, L) * 8 * (size_t)Bc))) return rc;
+    u64 *D = c->ws;
+    u64 *T1 = D + (size_t)Bc * L * N;
+    u64 *ACC = T1 + (size_t)Bc * L * (L + 1) * N;
+    u64 *T2 = ACC + (size_t)Bc * 2 * (L + 1) * N;
+    const u64 *key = (const u64 *)ksk;
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int bc = (B - b0) < Bc ? (B - b0) : Bc;
+        DView tgt{(u64 *)in->data + (u64)b0 * in->batch_stride + (mode == 1 ? 2 : 1) * in->poly_stride, in->batch_stride, 0};
+        DView base{(u64 *)in->data + (u64)b0 * in->batch_stride, in->batch_stride, in->poly_stride};
+        DView dst{(u64 *)out->data + (u64)b0 * out->batch_stride, out->batch_stride, out->poly_stride};
+        DView dD{D, (u64)L * N, 0};
+        DView spec{ACC + (size_t)L * N, (u64)(L + 1) * N, 0};             // special-prime limb of every (b,k)
+        DView minu{ACC, 2 * (u64)(L + 1) * N, (u64)(L + 1) * N};
+#define RUN(LN)                                                                                                         \
+    {                                                                                                                   \
+        typedef NttGeo<LN> G;                                                                                           \
+        if (mode == 2) k_ks_intt_row<LN, true><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(tgt, perm, D, L, c->t); \
+        else k_ks_intt_row<LN, false><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(tgt, perm, D, L, c->t);        \
+        LAUNCH_CHECK(c);                                                                                                \
+        k_inv_col<LN, false><<<dim3(G::COL_TILES, L, bc), NTT_THREADS, 0, st>>>(dD, dD, L, 0, c->t);                    \
+        LAUNCH_CHECK(c);                                                                                                \
+        k_ks_modup_col<LN><<<dim3(G::COL_TILES, L *(L + 1), bc), NTT_THREADS, 0, st>>>(D, T1, L, c->t);                 \
+        LAUNCH_CHECK(c);                                                                                                \
+        if (mode == 2) k_ks_mac<LN, true><<<dim3(G::ROW_TILES, L + 1, bc), NTT_THREADS, 0, st>>>(T1, tgt, perm, key, ACC, L, c->t); \
+        else k_ks_mac<LN, false><<<dim3(G::ROW_TILES, L + 1, bc), NTT_THREADS, 0, st>>>(T1, tgt, perm, key, ACC, L, c->t); \
+        LAUNCH_CHECK(c);                                                                                                \
+        k_inv_row<LN><<<dim3(G::ROW_TILES, 1, 2 * bc), NTT_THREADS, 0, st>>>(spec, spec, 1, K - 1, c->t);               \
+        LAUNCH_CHECK(c);                                                                                                \
+        k_inv_col<LN, true><<<dim3(G::COL_TILES, 1, 2 * bc), NTT_THREADS, 0, st>>>(spec, spec, 1, K - 1, c->t);         \
+        LAUNCH_CHECK(c);                                                                                                \
+        k_md_fwd_col<LN><<<dim3(G::COL_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(spec, T2, L, K - 1, c->t);              \
+        LAUNCH_CHECK(c);                                                                                                \
+        if (mode == 2) k_md_fwd_row<LN, 2><<<dim3(G::ROW_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(T2, minu, base, dst, perm, 2, L, K - 1, c->t); \
+        else k_md_fwd_row<LN, 1><<<dim3(G::ROW_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(T2, minu, base, dst, perm, 2, L, K - 1, c->t); \
+        LAUNCH_CHECK(c);                                                                                                \
+    }
+        DISPATCH_LOGN(c, RUN)
+#undef RUN
+    }
+    return CKKS_OK;
+}
+
+extern "C" int ckks_relinearize(ckks_ctx *c, const ckks_view *in, const uint64_t *rlk, const ckks_view *out, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, in, "encrypted")) || (rc = check_view(c, out, "out"))) return rc;
+    if (!rlk) return fail(CKKS_ERR_INVALID, "relin_keys is not valid for encryption parameters");
+    if (in->size != 3) return fail(CKKS_ERR_INVALID, "relinearize: only size-3 ciphertexts are supported");
+    if (out->size != 2 || out->batch != in->batch || out->limbs != in->limbs) return fail(CKKS_ERR_INVALID, "destination parameter mismatch");
+    if (out->data == in->data && (out->poly_stride != in->poly_stride || out->batch_stride != in->batch_stride))
+        return fail(CKKS_ERR_INVALID, "relinearize: in-place only with identical strides");
+    CU(cudaSetDevice(c->device));
+    return keyswitch(c, 1, in, nullptr, rlk, out, (cudaStream_t)s);
+}
+
+extern "C" int ckks_apply_galois(ckks_ctx *c, const ckks_view *in, uint64_t g, const uint64_t *gk, const ckks_view *out, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, in, "encrypted")) || (rc = check_view(c, out, "out"))) return rc;
+    if (!gk) return fail(CKKS_ERR_INVALID, "Galois key not present");
+    if (in->size != 2) return fail(CKKS_ERR_INVALID, "encrypted size must be 2");
+    if ((rc = same_shape(in, out, "destination"))) return rc;
+    if (out->data == in->data) return fail(CKKS_ERR_INVALID, "apply_galois: out must not alias in");
+    const uint32_t *perm = nullptr;
+    if ((rc = get_perm(c, g, &perm))) return rc;
+    CU(cudaSetDevice(c->device));
+    return keyswitch(c, 2, in, perm, gk, out, (cudaStream_t)s);
+}
+
+extern "C" int ckks_keyset_create(ckks_ctx *c, ckks_keyset **out) {
+    if (!c || !out) return fail(CKKS_ERR_INVALID, "null argument");
+    *out = new ckks_keyset{c};
+    return CKKS_OK;
+}
+extern "C" void ckks_keyset_destroy(ckks_keyset *ks) { delete ks; }
+extern "C" int ckks_keyset_set_relin(ckks_keyset *ks, const uint64_t *rlk) {
+    ks->relin = rlk;
+    return CKKS_OK;
+}
+extern "C" int ckks_keyset_set_galois(ckks_keyset *ks, uint64_t g, const uint64_t *gk) {
+    const uint32_t *perm = nullptr;
+    int rc = get_perm(ks->ctx, g, &perm);  // build the permutation table now (not capturable later)
+    if (rc) return rc;
+    ks->galois[g] = gk;
+    return CKKS_OK;
+}
+extern "C" int ckks_keyset_has_galois(const ckks_keyset *ks, uint64_t g) { return ks->galois.count(g) ? 1 : 0; }
+
+extern "C" int ckks_rotate(ckks_ctx *c, const ckks_keyset *ks, const ckks_view *in, int steps, const ckks_view *out,
+                           const ckks_view *scratch, ckks_stream s) {
+    int rc;
+    if (!ks) return fail(CKKS_ERR_INVALID, "null keyset");
+    if ((rc = check_view(c, in, "encrypted")) || (rc = check_view(c, out, "out")) || (rc = same_shape(in, out, "destination"))) return rc;
+    if (steps == 0) {  // SEAL: rotate by 0 returns the input unchanged
+        CU(cudaSetDevice(c->device));
+        k_ew_copy<<<ew_grid(c, in->size * in->limbs, in->batch), 256, 0, (cudaStream_t)s>>>(dv(in), dv(out), in->limbs, c->n);
+        LAUNCH_CHECK(c);
+        return CKKS_OK;
+    }
+    uint64_t g = ckks::galois_elt_from_step(c->log_n, steps);
+    if (!g) return fail(CKKS_ERR_INVALID, "step count too large");
+    auto it = ks->galois.find(g);
+    if (it != ks->galois.end()) return ckks_apply_galois(c, in, g, it->second, out, s);
+    // SEAL Evaluator::rotate_internal: NAF decomposition, terms applied least-significant first
+    std::vector<int> terms = ckks::naf_terms(steps), eff;
+    if (terms.size() == 1) return fail(CKKS_ERR_INVALID, "Galois key not present");
+    for (int tstep : terms)
+        if ((tstep < 0 ? -tstep : tstep) != c->n / 2) eff.push_back(tstep);
+    for (int tstep : eff) {
+        uint64_t gt = ckks::galois_elt_from_step(c->log_n, tstep);
+        if (!gt || !ks->galois.count(gt)) return fail(CKKS_ERR_INVALID, "Galois key not present");
+    }
+    if (eff.size() > 1) {
+        if ((rc = check_view(c, scratch, "scratch")) || (rc = same_shape(in, scratch, "scratch"))) return rc;
+        if (scratch->data == in->data || scratch->data == out->data) return fail(CKKS_ERR_INVALID, "scratch must be distinct storage");
+    }
+    const ckks_view *cur = in;
+    for (size_t i = 0; i < eff.size(); i++) {
+        const ckks_view *dstv = ((eff.size() - 1 - i) % 2 == 0) ? out : scratch;
+        uint64_t gt = ckks::galois_elt_from_step(c->log_n, eff[i]);
+        if ((rc = ckks_apply_galois(c, cur, gt, ks->galois.at(gt), dstv, s))) return rc;
+        cur = dstv;
+    }
+    return CKKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ rescale
+extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *out, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, in, "encrypted")) || (rc = check_view(c, out, "out"))) return rc;
+    if (in->limbs < 2) return fail(CKKS_ERR_INVALID, "end of modulus switching chain reached");
+    if (out->batch != in->batch || out->size != in->size || out->limbs != in->limbs - 1)
+        return fail(CKKS_ERR_INVALID, "destination parameter mismatch");
+    if (out->data == in->data && (out->poly_stride != in->poly_stride || out->batch_stride != in->batch_stride))
+        return fail(CKKS_ERR_INVALID, "rescale: in-place only with identical strides");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)s;
+    const int L = in->limbs, S = in->size, B = in->batch, Lo = L - 1;
+    const size_t N = c->n;
+    const size_t per = (size_t)S * N * (1 + Lo);
+    size_t fit = c->ws_cap / (per * 8);
+    if (fit < 1) fit = 1;
+    int Bc = (int)(fit < (size_t)B ? fit : (size_t)B);
+    while ((long)Bc * S > 65535) Bc--;
+    if ((rc = ensure_ws(c, per * 8 * Bc))) return rc;
+    u64 *R = c->ws, *T2 = R + (size_t)Bc * S * N;
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int bc = (B - b0) < Bc ? (B - b0) : Bc;
+        DView src{(u64 *)in->data + (u64)b0 * in->batch_stride, in->batch_stride, in->poly_stride};
+        DView last{src.data + (size_t)Lo * N, src.bs, src.ps};
+        DView dR{R, (u64)S * N, (u64)N};
+        DView Rz{R, (u64)N, 0};
+        DView dst{(u64 *)out->data + (u64)b0 * out->batch_stride, out->batch_stride, out->poly_stride};
+#define RUN(LN)                                                                                                   \
+    {                                                                                                             \
+        typedef NttGeo<LN> G;                                                                                     \
+        k_inv_row<LN><<<dim3(G::ROW_TILES, S, bc), NTT_THREADS, 0, st>>>(last, dR, 1, Lo, c->t);                  \
+        LAUNCH_CHECK(c);                                                                                          \
+        k_inv_col<LN, true><<<dim3(G::COL_TILES, S, bc), NTT_THREADS, 0, st>>>(dR, dR, 1, Lo, c->t);              \
+        LAUNCH_CHECK(c);                                                                                          \
+        k_md_fwd_col<LN><<<dim3(G::COL_TILES, Lo, bc * S), NTT_THREADS, 0, st>>>(Rz, T2, Lo, Lo, c->t);           \
+        LAUNCH_CHECK(c);                                                                                          \
+        k_md_fwd_row<LN, 0><<<dim3(G::ROW_TILES, Lo, bc * S), NTT_THREADS, 0, st>>>(T2, src, src, dst, nullptr, S, Lo, Lo, c->t); \
+        LAUNCH_CHECK(c);                                                                                          \
+    }
+        DISPATCH_LOGN(c, RUN)
+#undef RUN
+    }
+    return CKKS_OK;
+}

@@ -1,0 +1,380 @@
+// kernels.cuh -- sm_100a kernels of the CKKS evaluation engine.
+//
+// Families:
+//   * plain batched NTT / INTT (column + row pass per transform)
+//   * element-wise dyadic ops (add, sub, negate, multiply, multiply_plain, add_plain, add_many)
+//   * key switching: digit INTT (with the Galois gather fused into its load), mod-up base
+//     conversion fused into the column pass of the NTT, key inner product fused into the row
+//     pass, mod-down fused into the NTT passes of the special-prime limb
+//   * rescale: same mod-down machinery with the last data prime
+//
+// Grid conventions: blockIdx.x = tile inside a limb, blockIdx.y = limb / (digit,limb) pair,
+// blockIdx.z = ciphertext (or ciphertext*poly) index.  All CTAs are NTT_THREADS threads.
+#pragma once
+#include "ntt_passes.cuh"
+
+struct Tables {
+    const ModConst *mod;  // [K]
+    const tw_t *twf;      // [K][N] forward twiddles
+    const tw_t *twi;      // [K][N] inverse twiddles
+    const u64 *inv;       // [K][K]  inv[a*K+j]  = q_a^-1 mod q_j
+    const u64 *invs;      // [K][K]  Shoup companion
+    const u64 *halfmod;   // [K][K]  (q_a >> 1) mod q_j
+    int K;
+    int round_half;
+};
+
+struct DView {
+    u64 *data;
+    u64 bs;  // batch stride (words)
+    u64 ps;  // poly stride (words)
+};
+
+__device__ __forceinline__ ModConst load_mod(const Tables &t, int j) { return t.mod[j]; }
+
+// =============================================================================== plain NTT
+// limb instance y = s*limbs + l of batch entry z; prime = first_prime + l
+template <int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_col(DView src, DView dst, int limbs, int first_prime, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int s = blockIdx.y / limbs, l = blockIdx.y % limbs, pj = first_prime + l;
+    const u64 *in = src.data + blockIdx.z * src.bs + s * src.ps + (u64)l * G::N;
+    u64 *out = dst.data + blockIdx.z * dst.bs + s * dst.ps + (u64)l * G::N;
+    const ModConst m = load_mod(t, pj);
+    const int c0 = blockIdx.x * 32;
+    u64 x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = in[col_coarse_idx<LOGN>(c0, e)];
+    fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m.p, m.p2, smem);
+#pragma unroll
+    for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];  // lazy [0,4p)
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_row(DView src, DView dst, int limbs, int first_prime, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int s = blockIdx.y / limbs, l = blockIdx.y % limbs, pj = first_prime + l;
+    const u64 *in = src.data + blockIdx.z * src.bs + s * src.ps + (u64)l * G::N;
+    u64 *out = dst.data + blockIdx.z * dst.bs + s * dst.ps + (u64)l * G::N;
+    const ModConst m = load_mod(t, pj);
+    const int t0 = blockIdx.x * NTT_TILE;
+    u64 x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
+    fwd_row_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m.p, m.p2, t0, smem);
+#pragma unroll
+    for (int e = 0; e < 8; e++) out[t0 + row_contig_li(e)] = csub(csub(x[e], m.p2), m.p);
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_inv_row(DView src, DView dst, int limbs, int first_prime, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int s = blockIdx.y / limbs, l = blockIdx.y % limbs, pj = first_prime + l;
+    const u64 *in = src.data + blockIdx.z * src.bs + s * src.ps + (u64)l * G::N;
+    u64 *out = dst.data + blockIdx.z * dst.bs + s * dst.ps + (u64)l * G::N;
+    const ModConst m = load_mod(t, pj);
+    const int t0 = blockIdx.x * NTT_TILE;
+    u64 x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = in[t0 + row_contig_li(e)];
+    inv_row_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m.p, m.p2, t0, smem);
+#pragma unroll
+    for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = x[e];  // lazy [0,2p)
+}
+
+// ADD_HALF: store (v + (p >> 1)) mod p instead of v -- the "flooring to rounding" step of SEAL's
+// divide-by-last-prime, fused into the last pass of the inverse transform
+template <int LOGN, bool ADD_HALF>
+__global__ void __launch_bounds__(NTT_THREADS) k_inv_col(DView src, DView dst, int limbs, int first_prime, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int s = blockIdx.y / limbs, l = blockIdx.y % limbs, pj = first_prime + l;
+    const u64 *in = src.data + blockIdx.z * src.bs + s * src.ps + (u64)l * G::N;
+    u64 *out = dst.data + blockIdx.z * dst.bs + s * dst.ps + (u64)l * G::N;
+    const ModConst m = load_mod(t, pj);
+    const int c0 = blockIdx.x * 32;
+    u64 x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = in[col_fine_idx<LOGN>(c0, e)];
+    inv_col_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m, smem);
+    const u64 half = (ADD_HALF && t.round_half) ? (m.p >> 1) : 0;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        u64 v = csub(x[e], m.p);
+        if (ADD_HALF) v = csub(v + half, m.p);
+        out[col_coarse_idx<LOGN>(c0, e)] = v;
+    }
+}
+
+// =============================================================================== key switching
+// (1) digit INTT, row pass.  target limb i of ciphertext b: tgt.data + b*tgt.bs + i*N.
+// With GALOIS the Galois automorphism is applied while loading: in NTT form it is the pure
+// permutation out[g] = in[perm[g]] (SEAL util::apply_galois_ntt); perm maps each row of the
+// limb matrix into a single source row, so the gather stays inside one 0.5-4 KB segment.
+template <int LOGN, bool GALOIS>
+__global__ void __launch_bounds__(NTT_THREADS) k_ks_intt_row(DView tgt, const uint32_t *__restrict__ perm, u64 *D, int L, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int i = blockIdx.y, b = blockIdx.z;
+    const u64 *in = tgt.data + b * tgt.bs + (u64)i * G::N;
+    u64 *out = D + ((u64)b * L + i) * G::N;
+    const ModConst m = load_mod(t, i);
+    const int t0 = blockIdx.x * NTT_TILE;
+    u64 x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        int g = t0 + row_contig_li(e);
+        x[e] = in[GALOIS ? perm[g] : g];
+    }
+    inv_row_pass<LOGN>(x, t.twi + (size_t)i * G::N, m.p, m.p2, t0, smem);
+#pragma unroll
+    for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = x[e];
+}
+
+// (3) mod-up, column pass: digit i (coefficient form, canonical) reduced into prime pj and pushed
+// through the first six NTT stages.  y = i*(L+1) + jj; jj == L is the special prime.
+template <int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_ks_modup_col(const u64 *__restrict__ D, u64 *T1, int L, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int i = blockIdx.y / (L + 1), jj = blockIdx.y % (L + 1), b = blockIdx.z;
+    const int pj = jj == L ? t.K - 1 : jj;
+    if (pj == i) return;  // that limb is taken directly from the NTT-form target
+    const u64 *in = D + ((u64)b * L + i) * G::N;
+    u64 *out = T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N;
+    const ModConst m = load_mod(t, pj);
+    const int c0 = blockIdx.x * 32;
+    u64 x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = reduce64(in[col_coarse_idx<LOGN>(c0, e)], m);
+    fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m.p, m.p2, smem);
+#pragma unroll
+    for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
+}
+
+// (4) mod-up row pass fused with the key inner product: for output limb jj of ciphertext b,
+//     acc_k = sum_i NTT_pj(digit_i) (.) ksk[i][k][pj]     (k = 0,1), 128-bit lazy sums,
+// one Barrett reduction at the end.  Key limbs stream once from HBM, fully coalesced.
+template <int LOGN, bool GALOIS>
+__global__ void __launch_bounds__(NTT_THREADS) k_ks_mac(const u64 *__restrict__ T1, DView tgt, const uint32_t *__restrict__ perm,
+                                                        const u64 *__restrict__ ksk, u64 *ACC, int L, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int jj = blockIdx.y, b = blockIdx.z;
+    const int K = t.K, pj = jj == L ? K - 1 : jj;
+    const ModConst m = load_mod(t, pj);
+    const tw_t *tw = t.twf + (size_t)pj * G::N;
+    const int t0 = blockIdx.x * NTT_TILE;
+    u64 lo0[8], hi0[8], lo1[8], hi1[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) lo0[e] = hi0[e] = lo1[e] = hi1[e] = 0;
+    for (int i = 0; i < L; i++) {
+        u64 x[8];
+        if (i == pj) {
+            const u64 *in = tgt.data + b * tgt.bs + (u64)i * G::N;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                int g = t0 + row_contig_li(e);
+                x[e] = in[GALOIS ? perm[g] : g];
+            }
+        } else {
+            const u64 *in = T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N;
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
+            __syncthreads();  // previous iteration's shared-memory reads are done
+            fwd_row_pass<LOGN>(x, tw, m.p, m.p2, t0, smem);
+        }
+        const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+        const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            ulonglong2 a = __ldg(k0 + v), c = __ldg(k1 + v);
+            mac128(lo0[2 * v], hi0[2 * v], x[2 * v], a.x);
+            mac128(lo0[2 * v + 1], hi0[2 * v + 1], x[2 * v + 1], a.y);
+            mac128(lo1[2 * v], hi1[2 * v], x[2 * v], c.x);
+            mac128(lo1[2 * v + 1], hi1[2 * v + 1], x[2 * v + 1], c.y);
+        }
+    }
+    u64 *o0 = ACC + (((u64)b * 2 + 0) * (L + 1) + jj) * G::N + t0 + 8 * threadIdx.x;
+    u64 *o1 = ACC + (((u64)b * 2 + 1) * (L + 1) + jj) * G::N + t0 + 8 * threadIdx.x;
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        ulonglong2 r0, r1;
+        r0.x = barrett128(lo0[2 * v], hi0[2 * v], m);
+        r0.y = barrett128(lo0[2 * v + 1], hi0[2 * v + 1], m);
+        r1.x = barrett128(lo1[2 * v], hi1[2 * v], m);
+        r1.y = barrett128(lo1[2 * v + 1], hi1[2 * v + 1], m);
+        reinterpret_cast<ulonglong2 *>(o0)[v] = r0;
+        reinterpret_cast<ulonglong2 *>(o1)[v] = r1;
+    }
+}
+
+// (7) mod-down / rescale, column pass: R holds r' = (INTT(last limb) + half) mod q_a for poly
+// instance z; the value is carried into prime j as (r' mod q_j) - (half mod q_j) and pushed
+// through the first six NTT stages.  R limb of instance z: R.data + z*R.bs.
+template <int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_col(DView R, u64 *T2, int Lout, int a, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int j = blockIdx.y, z = blockIdx.z;
+    const u64 *in = R.data + z * R.bs;
+    u64 *out = T2 + ((u64)z * Lout + j) * G::N;
+    const ModConst m = load_mod(t, j);
+    const u64 hm = t.round_half ? t.halfmod[a * t.K + j] : 0;
+    const int c0 = blockIdx.x * 32;
+    u64 x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = submod(reduce64(in[col_coarse_idx<LOGN>(c0, e)], m), hm, m.p);
+    fwd_col_pass<LOGN>(x, t.twf + (size_t)j * G::N, m.p, m.p2, smem);
+#pragma unroll
+    for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
+}
+
+// (8) mod-down / rescale, row pass with the epilogue
+//     out = (minuend - NTT(u)) * q_a^-1  [+ base]          mod q_j
+// MODE 0 (rescale): no base.  MODE 1 (relinearize): base = in[b][k].  MODE 2 (Galois):
+// base = permuted in[b][0] for k == 0 and nothing for k == 1 (SEAL wipes c1 before switching).
+// z = b*S + s enumerates (ciphertext, poly).
+template <int LOGN, int MODE>
+__global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_row(const u64 *__restrict__ T2, DView minuend, DView base, DView dst,
+                                                            const uint32_t *__restrict__ perm, int S, int Lout, int a, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int j = blockIdx.y, z = blockIdx.z, b = z / S, s = z % S;
+    const u64 *in = T2 + ((u64)z * Lout + j) * G::N;
+    const ModConst m = load_mod(t, j);
+    const u64 qi = t.inv[a * t.K + j], qis = t.invs[a * t.K + j];
+    const int t0 = blockIdx.x * NTT_TILE;
+    u64 x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
+    fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m.p, m.p2, t0, smem);
+    const u64 *mi = minuend.data + b * minuend.bs + s * minuend.ps + (u64)j * G::N;
+    u64 *out = dst.data + b * dst.bs + s * dst.ps + (u64)j * G::N;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int g = t0 + row_contig_li(e);
+        u64 v = csub(csub(x[e], m.p2), m.p);
+        u64 r = shoup_mul(submod(mi[g], v, m.p), qi, qis, m.p);
+        if (MODE == 1) {
+            r = addmod(r, base.data[b * base.bs + s * base.ps + (u64)j * G::N + g], m.p);
+        } else if (MODE == 2) {
+            if (s == 0) r = addmod(r, base.data[b * base.bs + (u64)j * G::N + perm[g]], m.p);
+        }
+        out[g] = r;
+    }
+}
+
+// =============================================================================== element-wise
+// one thread = two adjacent coefficients of limb instance (z = batch, y = s*L + j)
+#define EW_PROLOGUE(LIMBS)                                                      \
+    const int s = blockIdx.y / (LIMBS), j = blockIdx.y % (LIMBS);               \
+    const u64 c = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 2;             \
+    if (c >= (u64)n) return;                                                    \
+    const ModConst m = t.mod[j];
+
+__device__ __forceinline__ const ulonglong2 *vp(const DView &v, int b, int s, int j, int n, u64 c) {
+    return reinterpret_cast<const ulonglong2 *>(v.data + b * v.bs + s * v.ps + (u64)j * n + c);
+}
+__device__ __forceinline__ ulonglong2 *vpw(const DView &v, int b, int s, int j, int n, u64 c) {
+    return reinterpret_cast<ulonglong2 *>(v.data + b * v.bs + s * v.ps + (u64)j * n + c);
+}
+
+// OP 0 add, 1 sub, 2 negate (b unused)
+template <int OP>
+__global__ void __launch_bounds__(256) k_ew_addsub(DView a, DView b, DView o, int L, int n, Tables t) {
+    EW_PROLOGUE(L)
+    ulonglong2 x = *vp(a, blockIdx.z, s, j, n, c), y, r;
+    if (OP != 2) y = *vp(b, blockIdx.z, s, j, n, c);
+    if (OP == 0) { r.x = addmod(x.x, y.x, m.p); r.y = addmod(x.y, y.y, m.p); }
+    if (OP == 1) { r.x = submod(x.x, y.x, m.p); r.y = submod(x.y, y.y, m.p); }
+    if (OP == 2) { r.x = x.x ? m.p - x.x : 0; r.y = x.y ? m.p - x.y : 0; }
+    *vpw(o, blockIdx.z, s, j, n, c) = r;
+}
+
+// every poly of ct times the plaintext (pt batch stride 0 = broadcast)
+__global__ void __launch_bounds__(256) k_ew_mul_plain(DView ct, DView pt, DView o, int L, int n, Tables t) {
+    EW_PROLOGUE(L)
+    ulonglong2 x = *vp(ct, blockIdx.z, s, j, n, c), y = *vp(pt, blockIdx.z, 0, j, n, c), r;
+    r.x = mulmod(x.x, y.x, m);
+    r.y = mulmod(x.y, y.y, m);
+    *vpw(o, blockIdx.z, s, j, n, c) = r;
+}
+
+// plain added to poly 0, other polys copied
+__global__ void __launch_bounds__(256) k_ew_add_plain(DView ct, DView pt, DView o, int L, int n, Tables t) {
+    EW_PROLOGUE(L)
+    ulonglong2 x = *vp(ct, blockIdx.z, s, j, n, c), r = x;
+    if (s == 0) {
+        ulonglong2 y = *vp(pt, blockIdx.z, 0, j, n, c);
+        r.x = addmod(x.x, y.x, m.p);
+        r.y = addmod(x.y, y.y, m.p);
+    }
+    *vpw(o, blockIdx.z, s, j, n, c) = r;
+}
+
+// ct x ct: out_k = sum_{i+l=k} a_i (.) b_l; sums kept in 128 bits, one reduction per output
+template <int SA, int SB>
+__global__ void __launch_bounds__(256) k_ew_multiply(DView a, DView b, DView o, int L, int n, Tables t) {
+    const int j = blockIdx.y;
+    const u64 c = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (c >= (u64)n) return;
+    const ModConst m = t.mod[j];
+    ulonglong2 xa[SA], xb[SB];
+#pragma unroll
+    for (int i = 0; i < SA; i++) xa[i] = *vp(a, blockIdx.z, i, j, n, c);
+#pragma unroll
+    for (int i = 0; i < SB; i++) xb[i] = *vp(b, blockIdx.z, i, j, n, c);
+#pragma unroll
+    for (int k = 0; k < SA + SB - 1; k++) {
+        u64 l0 = 0, h0 = 0, l1 = 0, h1 = 0;
+#pragma unroll
+        for (int i = 0; i < SA; i++) {
+            const int l = k - i;
+            if (l >= 0 && l < SB) {
+                mac128(l0, h0, xa[i].x, xb[l].x);
+                mac128(l1, h1, xa[i].y, xb[l].y);
+            }
+        }
+        ulonglong2 r;
+        r.x = barrett128(l0, h0, m);
+        r.y = barrett128(l1, h1, m);
+        *vpw(o, blockIdx.z, k, j, n, c) = r;
+    }
+}
+
+// out = in[0] + in[1] + ... + in[B-1]  (sequential modular adds, SEAL add_many order)
+__global__ void __launch_bounds__(256) k_ew_add_many(DView in, DView o, int B, int L, int n, Tables t) {
+    EW_PROLOGUE(L)
+    ulonglong2 acc = *vp(in, 0, s, j, n, c);
+    for (int b = 1; b < B; b++) {
+        ulonglong2 y = *vp(in, b, s, j, n, c);
+        acc.x = addmod(acc.x, y.x, m.p);
+        acc.y = addmod(acc.y, y.y, m.p);
+    }
+    *vpw(o, 0, s, j, n, c) = acc;
+}
+
+// strided limb copy (mod-switch drop into a differently laid out view)
+__global__ void __launch_bounds__(256) k_ew_copy(DView a, DView o, int L, int n) {
+    const int s = blockIdx.y / L, j = blockIdx.y % L;
+    const u64 c = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (c >= (u64)n) return;
+    *vpw(o, blockIdx.z, s, j, n, c) = *vp(a, blockIdx.z, s, j, n, c);
+}
+
+__global__ void k_fill_i32(int32_t *p, int n, int32_t v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// flags[b] cleared when any word of polys 1.. of entry b is non-zero
+__global__ void __launch_bounds__(256) k_transparent(DView ct, int32_t *flags, int L, int n) {
+    const int s = 1 + blockIdx.y / L, j = blockIdx.y % L;
+    const u64 c = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (c >= (u64)n) return;
+    ulonglong2 x = *vp(ct, blockIdx.z, s, j, n, c);
+    if (x.x | x.y) flags[blockIdx.z] = 0;
+}

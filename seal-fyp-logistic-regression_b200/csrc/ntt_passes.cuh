@@ -1,0 +1,204 @@
+// ntt_passes.cuh -- negacyclic NTT building blocks for one RNS limb of N = 2^LOGN words.
+//
+// A limb is viewed as an N1 x N2 row-major matrix (N1 = 64 rows, N2 = N/64 columns):
+//
+//   forward (Cooley-Tukey, natural in -> bit-reversed out, SEAL's order)
+//     column pass : stages 0..5   act along the rows index r for a fixed column c
+//     row pass    : stages 6..n-1 act inside each contiguous row of N2 words
+//   inverse (Gentleman-Sande) runs the same stages backwards: row pass, then column pass.
+//
+// Every CTA is 256 threads and owns 2048 words (16 KB of shared memory): a 64 x 32 column
+// tile, or 2048/N2 whole rows.  Each thread keeps 8 words in registers and performs up to
+// three radix-2 stages (a radix-8 step) between shared-memory exchanges, so a column pass
+// has one exchange and a row pass two.  Twiddles follow the binary tree of SEAL's table:
+// the butterfly of stage s on global index g uses node 2^s + (g >> (n - s)); a radix-8 step
+// rooted at node nd touches nodes nd, 2nd..2nd+1, 4nd..4nd+3.
+//
+// The passes are device functions working on a register array so that callers can fuse their
+// own loads (Galois gather, base conversion) and epilogues (key inner product, mod-down).
+#pragma once
+#include "modarith.cuh"
+
+#define NTT_THREADS 256
+#define NTT_TILE 2048
+
+template <int LOGN>
+struct NttGeo {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int N2LOG = LOGN - 6;
+    static constexpr int N2 = 1 << N2LOG;  // words per row
+    static constexpr int T = N2 / 8;       // threads per row in the row pass
+    static constexpr int REM = N2LOG - 6;  // stages left for the third radix step (0..3)
+    static constexpr int ROW_TILES = N / NTT_TILE;
+    static constexpr int COL_TILES = N2 / 32;
+    static_assert(LOGN >= 12 && LOGN <= 15, "supported degrees: 4096..32768");
+};
+
+typedef ulonglong2 tw_t;  // {w, floor(w 2^64 / p)}
+
+// swizzled shared-memory index for the row pass: keeps every access pattern of the three radix
+// steps conflict-free for 64-bit words (bank pair = low 4 bits)
+__device__ __forceinline__ int sw(int li) { return li ^ ((li >> 3) & 15); }
+
+// ---- radix-8 register steps ------------------------------------------------------------------
+// element e of x sits at global index base + e*stride; SKIP leading (coarse) stages are omitted
+template <int SKIP>
+__device__ __forceinline__ void fwd8(u64 (&x)[8], const tw_t *__restrict__ tw, unsigned nd, u64 p, u64 p2) {
+    if (SKIP < 1) {
+        tw_t w = __ldg(tw + nd);
+#pragma unroll
+        for (int e = 0; e < 4; e++) ct_bfly(x[e], x[e + 4], w.x, w.y, p, p2);
+    }
+    if (SKIP < 2) {
+        tw_t w0 = __ldg(tw + 2 * nd), w1 = __ldg(tw + 2 * nd + 1);
+        ct_bfly(x[0], x[2], w0.x, w0.y, p, p2);
+        ct_bfly(x[1], x[3], w0.x, w0.y, p, p2);
+        ct_bfly(x[4], x[6], w1.x, w1.y, p, p2);
+        ct_bfly(x[5], x[7], w1.x, w1.y, p, p2);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        tw_t w = __ldg(tw + 4 * nd + q);
+        ct_bfly(x[2 * q], x[2 * q + 1], w.x, w.y, p, p2);
+    }
+}
+
+template <int SKIP>
+__device__ __forceinline__ void inv8(u64 (&x)[8], const tw_t *__restrict__ tw, unsigned nd, u64 p, u64 p2) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        tw_t w = __ldg(tw + 4 * nd + q);
+        gs_bfly(x[2 * q], x[2 * q + 1], w.x, w.y, p, p2);
+    }
+    if (SKIP < 2) {
+        tw_t w0 = __ldg(tw + 2 * nd), w1 = __ldg(tw + 2 * nd + 1);
+        gs_bfly(x[0], x[2], w0.x, w0.y, p, p2);
+        gs_bfly(x[1], x[3], w0.x, w0.y, p, p2);
+        gs_bfly(x[4], x[6], w1.x, w1.y, p, p2);
+        gs_bfly(x[5], x[7], w1.x, w1.y, p, p2);
+    }
+    if (SKIP < 1) {
+        tw_t w = __ldg(tw + nd);
+#pragma unroll
+        for (int e = 0; e < 4; e++) gs_bfly(x[e], x[e + 4], w.x, w.y, p, p2);
+    }
+}
+
+// ---- column pass -------------------------------------------------------------------------------
+// tile = 64 rows x 32 columns starting at column c0; warp k (0..7), lane = column offset.
+// element e <-> row  (k + 8e)  on the coarse side   (stride 8 rows)
+//               row  (8k + e)  on the fine side     (stride 1 row)
+template <int LOGN>
+__device__ __forceinline__ int col_coarse_idx(int c0, int e) {
+    int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    return (k + 8 * e) * NttGeo<LOGN>::N2 + c0 + lane;
+}
+template <int LOGN>
+__device__ __forceinline__ int col_fine_idx(int c0, int e) {
+    int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    return (8 * k + e) * NttGeo<LOGN>::N2 + c0 + lane;
+}
+
+// forward: x holds the coarse-side elements (values < 4p); returns fine-side elements in [0,4p)
+template <int LOGN>
+__device__ __forceinline__ void fwd_col_pass(u64 (&x)[8], const tw_t *__restrict__ tw, u64 p, u64 p2, u64 *smem) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    fwd8<0>(x, tw, 1u, p, p2);  // stages 0..2, root node
+#pragma unroll
+    for (int e = 0; e < 8; e++) smem[(k + 8 * e) * 32 + lane] = x[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = smem[(8 * k + e) * 32 + lane];
+    fwd8<0>(x, tw, 8u + k, p, p2);  // stages 3..5
+}
+
+// inverse: x holds fine-side elements in [0,2p); returns coarse-side elements, scaled by N^-1,
+// in [0,2p)
+template <int LOGN>
+__device__ __forceinline__ void inv_col_pass(u64 (&x)[8], const tw_t *__restrict__ twi, const ModConst &m, u64 *smem) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u64 p = m.p, p2 = m.p2;
+    inv8<0>(x, twi, 8u + k, p, p2);  // stages 5..3
+#pragma unroll
+    for (int e = 0; e < 8; e++) smem[(8 * k + e) * 32 + lane] = x[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = smem[(k + 8 * e) * 32 + lane];
+    inv8<1>(x, twi, 1u, p, p2);  // stages 2..1
+    // stage 0 with N^-1 folded into both outputs
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        u64 s = x[e] + x[e + 4];
+        u64 d = x[e] + p2 - x[e + 4];
+        x[e] = shoup_lazy(s, m.ninv, m.ninvs, p);
+        x[e + 4] = shoup_lazy(d, m.w1ni, m.w1nis, p);
+    }
+}
+
+// ---- row pass ---------------------------------------------------------------------------------
+// tile = 2048 contiguous words starting at global index t0 (a whole number of rows).
+// strided side : element e <-> local index rr*N2 + k + T*e       (rr = tid / T, k = tid % T)
+// contiguous   : element e <-> local index 8*tid + e
+template <int LOGN>
+__device__ __forceinline__ int row_strided_li(int e) {
+    typedef NttGeo<LOGN> G;
+    int rr = threadIdx.x / G::T, k = threadIdx.x % G::T;
+    return rr * G::N2 + k + G::T * e;
+}
+__device__ __forceinline__ int row_contig_li(int e) { return 8 * (int)threadIdx.x + e; }
+
+template <int LOGN>
+__device__ __forceinline__ int row_mid_li(int e) {
+    typedef NttGeo<LOGN> G;
+    constexpr int T8 = G::T / 8;  // stride of the middle radix step
+    int rr = threadIdx.x / G::T, k = threadIdx.x % G::T;
+    int a = k / T8, k2 = k % T8;
+    return rr * G::N2 + a * G::T + k2 + T8 * e;
+}
+
+// forward: x = strided-side elements (< 4p) -> contiguous-side elements in [0,4p)
+template <int LOGN>
+__device__ __forceinline__ void fwd_row_pass(u64 (&x)[8], const tw_t *__restrict__ tw, u64 p, u64 p2, int t0, u64 *smem) {
+    typedef NttGeo<LOGN> G;
+    // stages 6..8
+    fwd8<0>(x, tw, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)), p, p2);
+#pragma unroll
+    for (int e = 0; e < 8; e++) smem[sw(row_strided_li<LOGN>(e))] = x[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = smem[sw(row_mid_li<LOGN>(e))];
+    // stages 9..11
+    fwd8<0>(x, tw, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)), p, p2);
+    if (G::REM > 0) {
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; e++) smem[sw(row_mid_li<LOGN>(e))] = x[e];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = smem[sw(row_contig_li(e))];
+        // last REM stages; virtual root stage is n-3
+        fwd8<3 - (G::REM > 0 ? G::REM : 3)>(x, tw, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3), p, p2);
+    }
+}
+
+// inverse: x = contiguous-side elements in [0,2p) -> strided-side elements in [0,2p)
+template <int LOGN>
+__device__ __forceinline__ void inv_row_pass(u64 (&x)[8], const tw_t *__restrict__ twi, u64 p, u64 p2, int t0, u64 *smem) {
+    typedef NttGeo<LOGN> G;
+    if (G::REM > 0) {
+        inv8<3 - (G::REM > 0 ? G::REM : 3)>(x, twi, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3), p, p2);
+#pragma unroll
+        for (int e = 0; e < 8; e++) smem[sw(row_contig_li(e))] = x[e];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = smem[sw(row_mid_li<LOGN>(e))];
+    }
+    inv8<0>(x, twi, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)), p, p2);
+    if (G::REM > 0) __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) smem[sw(row_mid_li<LOGN>(e))] = x[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = smem[sw(row_strided_li<LOGN>(e))];
+    inv8<0>(x, twi, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)), p, p2);
+}

@@ -1,0 +1,256 @@
+"""GPU parity tests: every evaluator op of the CUDA path, through the C ABI, bit-exact against
+the CPU oracle on identical seeded inputs and keys.  Uniform random residues are valid inputs
+for every op (the evaluator is a deterministic function of limbs and keys), so bit-exactness is
+checked on those; decrypt/decode semantics are checked separately within a stated tolerance."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CHAINS = {
+    12: [50, 40, 40, 50],
+    13: [60, 40, 40, 60],
+    14: [60, 40, 40, 40, 40, 60],
+    15: [60, 40, 40, 40, 60],
+}
+
+
+@pytest.mark.parametrize("log_n", [12, 13, 14, 15])
+def test_ntt_bit_exact_all_primes(make_fixture, eng, log_n):
+    import torch
+    fx = make_fixture(log_n, CHAINS[log_n])
+    rng = np.random.default_rng(log_n)
+    K = len(fx.primes)
+    a = np.stack([rng.integers(0, p, size=(3, fx.n), dtype=np.uint64) for p in fx.primes], axis=1)  # [3][K][N]
+    a[0, :, :] = 0
+    a[0, :, 1] = 1                      # x -> twiddle pattern
+    a[1] = np.array(fx.primes, dtype=np.uint64)[:, None] - 1   # maximum residues
+    want = np.stack([np.stack([fx.orc.ntt(j, a[i, j]) for j in range(K)]) for i in range(3)])
+    t = torch.from_numpy(a.view(np.int64).copy()).cuda()
+    fx.ev.ntt_forward(t)
+    got = t.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)
+    fx.ev.ntt_inverse(t)
+    assert np.array_equal(t.cpu().numpy().view(np.uint64), a)
+    # inverse alone vs oracle
+    t2 = torch.from_numpy(a.view(np.int64).copy()).cuda()
+    fx.ev.ntt_inverse(t2)
+    want_i = np.stack([np.stack([fx.orc.intt(j, a[i, j]) for j in range(K)]) for i in range(3)])
+    assert np.array_equal(t2.cpu().numpy().view(np.uint64), want_i)
+
+
+def test_ntt_bfv_default_primes(po, eng):
+    """config 2 chains: SEAL's BFVDefault primes for N = 4096 / 8192 (benchmark.cpp:137)"""
+    import torch
+    for log_n in (12, 13):
+        primes = po.bfv_default(log_n)
+        orc = po.Oracle(log_n, primes)
+        ctx = eng.Context(log_n, primes)
+        ev = eng.Evaluator(ctx)
+        rng = np.random.default_rng(7)
+        a = np.stack([rng.integers(0, p, size=(1 << log_n), dtype=np.uint64) for p in primes])[None]
+        t = torch.from_numpy(a.view(np.int64).copy()).cuda()
+        ev.ntt_forward(t)
+        want = np.stack([orc.ntt(j, a[0, j]) for j in range(len(primes))])[None]
+        assert np.array_equal(t.cpu().numpy().view(np.uint64), want)
+
+
+@pytest.mark.parametrize("log_n", [12, 13])
+def test_elementwise_bit_exact(make_fixture, log_n):
+    fx = make_fixture(log_n, CHAINS[log_n])
+    rng = np.random.default_rng(11)
+    o, ev, ctx = fx.orc, fx.ev, fx.ctx
+    for L in (fx.L, 1):
+        a = fx.random_ct(rng, 3, 2, L)
+        b = fx.random_ct(rng, 3, 2, L)
+        a[0, 0, 0, :4] = 0                               # zero / negate edge
+        b[0, 0, 0, :4] = np.uint64(fx.primes[0] - 1)
+        da, db = ctx.upload(a), ctx.upload(b)
+        assert np.array_equal(ev.add(da, db).numpy(), np.stack([o.add(a[i], b[i]) for i in range(3)]))
+        assert np.array_equal(ev.sub(da, db).numpy(), np.stack([o.sub(a[i], b[i]) for i in range(3)]))
+        assert np.array_equal(ev.negate_inplace(da.clone()).numpy(), np.stack([o.negate(a[i]) for i in range(3)]))
+        assert np.array_equal(ev.multiply(da, db).numpy(), np.stack([o.multiply(a[i], b[i]) for i in range(3)]))
+        # size 3 x size 2 and 3 x 3 (Linear_Transform_Cipher sums size-3 products, helper.h:222-233)
+        a3 = fx.random_ct(rng, 3, 3, L)
+        d3 = ctx.upload(a3)
+        assert np.array_equal(ev.multiply(d3, db).numpy(), np.stack([o.multiply(a3[i], b[i]) for i in range(3)]))
+        assert np.array_equal(ev.add(d3, d3).numpy(), np.stack([o.add(a3[i], a3[i]) for i in range(3)]))
+        # plaintext ops: broadcast and per-entry plaintexts
+        p1 = fx.random_ct(rng, 1, 1, L)
+        p3 = fx.random_ct(rng, 3, 1, L)
+        dp1, dp3 = ctx.upload(p1), ctx.upload(p3)
+        assert np.array_equal(ev.multiply_plain(da, dp1).numpy(), np.stack([o.multiply_plain(a[i], p1[0, 0]) for i in range(3)]))
+        assert np.array_equal(ev.multiply_plain(da, dp3).numpy(), np.stack([o.multiply_plain(a[i], p3[i, 0]) for i in range(3)]))
+        assert np.array_equal(ev.add_plain(da, dp1).numpy(), np.stack([o.add_plain(a[i], p1[0, 0]) for i in range(3)]))
+        # add_many = sequential adds
+        want = a[0]
+        for i in range(1, 3):
+            want = o.add(want, a[i])
+        assert np.array_equal(ev.add_many(da).numpy()[0], want)
+
+
+@pytest.mark.parametrize("log_n", [12, 13, 14, 15])
+def test_relinearize_bit_exact(make_fixture, log_n):
+    fx = make_fixture(log_n, CHAINS[log_n])
+    rng = np.random.default_rng(21)
+    levels = (fx.L, 1) if log_n > 12 else tuple(range(fx.L, 0, -1))
+    for L in levels:
+        a = fx.random_ct(rng, 2, 3, L)
+        got = fx.ev.relinearize(fx.ctx.upload(a), fx.keys).numpy()
+        want = np.stack([fx.orc.relinearize(a[i], fx.rlk) for i in range(2)])
+        assert np.array_equal(got, want), (log_n, L)
+
+
+@pytest.mark.parametrize("log_n", [12, 13, 14, 15])
+def test_apply_galois_bit_exact(make_fixture, log_n):
+    fx = make_fixture(log_n, CHAINS[log_n])
+    rng = np.random.default_rng(22)
+    levels = (fx.L, 1) if log_n > 12 else tuple(range(fx.L, 0, -1))
+    for L in levels:
+        a = fx.random_ct(rng, 2, 2, L)
+        d = fx.ctx.upload(a)
+        for step in ((1, -8) if log_n > 12 else (1, -1, 2, 4, -8)):
+            g = fx.orc.galois_elt(step)
+            got = fx.ev.apply_galois(d, g, fx.keys).numpy()
+            want = np.stack([fx.orc.apply_galois(a[i], g, fx.gks[g]) for i in range(2)])
+            assert np.array_equal(got, want), (log_n, L, step)
+
+
+def test_rotate_vector_naf_chain(make_fixture):
+    """composite steps go through SEAL's NAF decomposition, least-significant term first"""
+    fx = make_fixture(12, CHAINS[12], steps=(1, -1, 2, -2, 4, -4, 8, -8, 16))
+    rng = np.random.default_rng(23)
+    a = fx.random_ct(rng, 2, 2, fx.L)
+    d = fx.ctx.upload(a)
+    for step in (3, 7, -3, 5, 11, 13, -6, 0):
+        got = fx.ev.rotate_vector(d, step, fx.keys).numpy()
+        want = np.stack([fx.orc.rotate(a[i], step, fx.gks) for i in range(2)])
+        assert np.array_equal(got, want), step
+    from importlib import import_module
+    capi = import_module("seal-fyp-logistic-regression_b200.capi")
+    with pytest.raises(capi.CkksInvalidArgument):
+        fx.ev.rotate_vector(d, 32, fx.keys)          # power of two without a key: "Galois key not present"
+    with pytest.raises(capi.CkksInvalidArgument):
+        fx.ev.rotate_vector(d, fx.n // 2, fx.keys)   # "step count too large"
+
+
+@pytest.mark.parametrize("log_n", [12, 13, 14, 15])
+def test_rescale_bit_exact(make_fixture, log_n):
+    fx = make_fixture(log_n, CHAINS[log_n])
+    rng = np.random.default_rng(24)
+    for L in range(fx.L, 1, -1):
+        for S in (2, 3):
+            a = fx.random_ct(rng, 2, S, L)
+            got = fx.ev.rescale_to_next(fx.ctx.upload(a))
+            want = np.stack([fx.orc.rescale(a[i]) for i in range(2)])
+            assert got.limbs == L - 1
+            assert np.array_equal(got.numpy(), want), (log_n, L, S)
+    # in place, with limb capacity kept
+    a = fx.random_ct(rng, 1, 2, fx.L)
+    d = fx.ctx.upload(a)
+    fx.ev.rescale_to_next_inplace(d)
+    assert np.array_equal(d.numpy()[0], fx.orc.rescale(a[0]))
+
+
+def test_rounding_switch_matches_oracle(make_fixture):
+    fx = make_fixture(12, CHAINS[12])
+    rng = np.random.default_rng(25)
+    a = fx.random_ct(rng, 1, 2, fx.L)
+    a3 = fx.random_ct(rng, 1, 3, fx.L)
+    try:
+        fx.ctx.set_rounding(False)
+        fx.orc.set_rounding(False)
+        assert np.array_equal(fx.ev.rescale_to_next(fx.ctx.upload(a)).numpy()[0], fx.orc.rescale(a[0]))
+        assert np.array_equal(fx.ev.relinearize(fx.ctx.upload(a3), fx.keys).numpy()[0], fx.orc.relinearize(a3[0], fx.rlk))
+    finally:
+        fx.ctx.set_rounding(True)
+        fx.orc.set_rounding(True)
+
+
+def test_batched_equals_single_and_chunked_workspace(make_fixture):
+    """a batch is processed exactly like its entries one by one, also when the workspace cap
+    forces the key switch to run in chunks"""
+    fx = make_fixture(12, CHAINS[12])
+    rng = np.random.default_rng(26)
+    a = fx.random_ct(rng, 7, 2, fx.L)
+    d = fx.ctx.upload(a)
+    g = fx.orc.galois_elt(1)
+    full = fx.ev.apply_galois(d, g, fx.keys).numpy()
+    fx.ctx.set_workspace_cap(3 * 8 * fx.n * 40)      # room for ~2 ciphertexts per chunk
+    try:
+        chunked = fx.ev.apply_galois(d, g, fx.keys).numpy()
+    finally:
+        fx.ctx.set_workspace_cap(1 << 30)
+    assert np.array_equal(full, chunked)
+    for i in range(7):
+        assert np.array_equal(fx.ev.apply_galois(d[i], g, fx.keys).numpy()[0], full[i])
+
+
+def test_end_to_end_semantics_and_errors(make_fixture, po):
+    """encrypt -> GPU evaluate -> decrypt/decode vs plaintext math, |err| < 2^-20 relative at
+    scale 2^40 (north star tolerance); plus SEAL's error behaviour"""
+    from importlib import import_module
+    capi = import_module("seal-fyp-logistic-regression_b200.capi")
+    fx = make_fixture(13, CHAINS[13])
+    o, ev, ctx = fx.orc, fx.ev, fx.ctx
+    rng = np.random.default_rng(27)
+    scale = 2.0 ** 40
+    x, y = rng.uniform(-1, 1, 128), rng.uniform(-1, 1, 128)
+    cx = o.encrypt(30, fx.pk, o.encode(x, scale))
+    cy = o.encrypt(31, fx.pk, o.encode(y, scale))
+    dx, dy = ctx.upload(cx, scale=scale), ctx.upload(cy, scale=scale)
+    prod = ev.rescale_to_next(ev.relinearize(ev.multiply(dx, dy), fx.keys))
+    dec = o.decode(o.decrypt(fx.sk, prod.numpy()[0]), prod.scale)[:128]
+    tol = 2.0 ** -20
+    assert np.abs(dec - x * y).max() < tol * max(1.0, np.abs(x * y).max())
+    rot = ev.rotate_vector(dx, 1, fx.keys)
+    full = np.zeros(fx.n // 2)
+    full[:128] = x
+    dec = o.decode(o.decrypt(fx.sk, rot.numpy()[0]), scale)
+    assert np.abs(dec - np.roll(full, -1)).max() < tol
+    # scale mismatch / level mismatch / scale out of bounds / end of chain / transparent
+    with pytest.raises(capi.CkksInvalidArgument, match="scale mismatch"):
+        ev.add(dx, ev.multiply_plain(dy, ctx.upload_plain(o.encode(1.0, scale), scale=scale)))
+    low = ev.mod_switch_to(dy, dy.limbs - 1)
+    with pytest.raises(capi.CkksInvalidArgument, match="parameter mismatch"):
+        ev.add(dx, low)
+    big = ev.multiply(dx, dy)
+    big2 = ev.relinearize(big, fx.keys)
+    with pytest.raises(capi.CkksInvalidArgument, match="scale out of bounds"):
+        ev.multiply(ev.multiply(big2, big2), big2)
+    one = ev.mod_switch_to(dx, 1)
+    with pytest.raises(capi.CkksInvalidArgument, match="end of modulus switching chain"):
+        ev.rescale_to_next(one)
+    zero = ctx.upload_plain(np.zeros((fx.L, fx.n), dtype=np.uint64), scale=scale)
+    with pytest.raises(capi.CkksLogicError, match="transparent"):
+        ev.multiply_plain(dx, zero, check_transparent=True)
+    with pytest.raises(capi.CkksInvalidArgument):
+        ev.rotate_vector(dx, 3 * 1024 + 5, eng_keys_without(fx))
+
+
+def eng_keys_without(fx):
+    return fx.eng.KeySet(fx.ctx)
+
+
+def test_full_size_properties_n32768(make_fixture):
+    """BASELINE config 5 size (N = 32768): besides the direct oracle comparison above, a
+    size-independent property -- for ANY input polynomials, Dec(apply_galois(ct)) equals the
+    automorphism of Dec(ct) up to key-switch noise (a few thousand units against 2^60 moduli)."""
+    fx = make_fixture(15, CHAINS[15])
+    rng = np.random.default_rng(28)
+    L = fx.L
+    a = fx.random_ct(rng, 2, 2, L)
+    da = fx.ctx.upload(a)
+    for step in (1, -8):
+        g = fx.orc.galois_elt(step)
+        ra = fx.ev.apply_galois(da, g, fx.keys).numpy()
+        for i in range(2):
+            m = fx.orc.decrypt(fx.sk, a[i])
+            mr = fx.orc.decrypt(fx.sk, ra[i])
+            for j in range(L):
+                p = fx.primes[j]
+                want = fx.orc.galois_permute(g, m[j])
+                diff = (mr[j].astype(object) - want.astype(object)) % p
+                c = fx.orc.intt(j, np.array(diff, dtype=np.uint64)).astype(object)
+                c = np.where(c > p // 2, c - p, c)
+                assert np.abs(c).max() < 2 ** 24, (step, i, j)
