@@ -142,6 +142,28 @@ int ckks_keyset_has_galois(const ckks_keyset *ks, uint64_t galois_elt);
 int ckks_rotate(ckks_ctx *ctx, const ckks_keyset *ks, const ckks_view *in, int steps, const ckks_view *out,
                 const ckks_view *scratch, ckks_stream s);
 
+/* Rotation plan: a fixed list of step counts, one per batch entry, compiled once into rounds so
+ * that the d-1 different rotations of a Halevi-Shoup linear transform (helper.h:252-257) run as a
+ * few batched key switches instead of d-1 dependent calls.  Each entry follows exactly SEAL's
+ * rotate_vector for its step (direct key, else NAF terms least-significant first). */
+typedef struct ckks_rotplan ckks_rotplan;
+int ckks_rotplan_create(ckks_ctx *ctx, ckks_keyset *ks, const int *steps, int batch, ckks_rotplan **out);
+void ckks_rotplan_destroy(ckks_rotplan *plan);
+uint64_t ckks_rotplan_keyswitches(const ckks_rotplan *plan); /* total Galois key switches per run */
+int ckks_rotplan_rounds(const ckks_rotplan *plan);
+/* in->batch is the plan's batch, or 1 to rotate one ciphertext by every step of the plan;
+ * out and scratch (needed when some entry has more than one NAF term) are plan-batch views */
+int ckks_rotate_plan(ckks_ctx *ctx, const ckks_rotplan *plan, const ckks_view *in, const ckks_view *out,
+                     const ckks_view *scratch, ckks_stream s);
+
+/* ---- fused multiply + add_many (bit-identical to the sequential ops: sums are modulo q)
+ * out (batch 1) = sum_b cts[b] (.) pts[b]        -- multiply_plain + add_many, helper.h:250-259 */
+int ckks_multiply_plain_sum(ckks_ctx *ctx, const ckks_view *cts, const ckks_view *pts, const ckks_view *out,
+                            ckks_stream s);
+/* out (batch 1, size 3) = sum_b a[b] x b[b] for size-2 inputs -- multiply + add_many,
+ * helper.h:222-233, matrix_multiplication.cpp:123-129 */
+int ckks_multiply_sum(ckks_ctx *ctx, const ckks_view *a, const ckks_view *b, const ckks_view *out, ckks_stream s);
+
 /* ---- rescale / mod switch */
 /* Evaluator::rescale_to_next_inplace (helper.h:441,543; matrix_multiplication.cpp:71-72):
  * out->limbs == in->limbs - 1.  out may alias in when strides are identical. */

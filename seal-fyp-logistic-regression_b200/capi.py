@@ -74,6 +74,13 @@ SIGNATURES = {
     "ckks_keyset_set_galois": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "ckks_keyset_has_galois": (C.c_int, [C.c_void_p, C.c_uint64]),
     "ckks_rotate": (C.c_int, [C.c_void_p, C.c_void_p, _VP, C.c_int, _VP, _VP, C.c_void_p]),
+    "ckks_rotplan_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_int, _vpp]),
+    "ckks_rotplan_destroy": (None, [C.c_void_p]),
+    "ckks_rotplan_keyswitches": (C.c_uint64, [C.c_void_p]),
+    "ckks_rotplan_rounds": (C.c_int, [C.c_void_p]),
+    "ckks_rotate_plan": (C.c_int, [C.c_void_p, C.c_void_p, _VP, _VP, _VP, C.c_void_p]),
+    "ckks_multiply_plain_sum": (C.c_int, [C.c_void_p, _VP, _VP, _VP, C.c_void_p]),
+    "ckks_multiply_sum": (C.c_int, [C.c_void_p, _VP, _VP, _VP, C.c_void_p]),
     "ckks_rescale": (C.c_int, [C.c_void_p, _VP, _VP, C.c_void_p]),
     "ckks_mod_switch_drop": (C.c_int, [C.c_void_p, _VP, _VP, C.c_void_p]),
 }

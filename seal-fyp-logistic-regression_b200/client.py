@@ -1,8 +1,8 @@
 """Client-side objects the reference builds around the Evaluator: CKKSEncoder, KeyGenerator,
 Encryptor, Decryptor (reference: logistic_regression_ckks.cpp:426-441, helper.h callers).
 
-These sit *beside* the hot path.  Ring arithmetic runs on the GPU
-through the C ABI (NTT, dyadic products, divide-by-last-prime); the host only samples
+These sit *beside* the hot path.  All ring arithmetic runs on the
+GPU through the C ABI (NTT, dyadic products, divide-by-last-prime); the host only samples
 randomness (numpy) and does the floating-point embedding / CRT composition.  Results are
 compared with tolerance, never bit-exactly (SEAL's own randomness is unpinned).
 """
@@ -19,6 +19,14 @@ def _bitrev(x, bits):
         r = (r << np.uint64(1)) | (x & np.uint64(1))
         x = x >> np.uint64(1)
     return r
+
+
+def galois_perm(log_n, g):
+    """index table of the NTT-domain automorphism: out[i] = in[perm[i]]"""
+    n = 1 << log_n
+    i = np.arange(n, dtype=np.uint64)
+    e = (np.uint64(g) * (np.uint64(2) * _bitrev(i, log_n) + np.uint64(1))) & np.uint64(2 * n - 1)
+    return _bitrev((e - np.uint64(1)) >> np.uint64(1), log_n).astype(np.int64)
 
 
 class CKKSEncoder:
@@ -42,10 +50,9 @@ class CKKSEncoder:
         return self.slots
 
     def _to_residues(self, coeffs, limbs):
-        """integer-valued float64 / python-int coefficients -> [limbs][N] uint64 residues"""
+        """integer-valued float64 coefficients -> [limbs][N] uint64 residues"""
         out = np.empty((limbs, self.ctx.n), dtype=np.uint64)
-        big = np.abs(coeffs).max() >= 2.0 ** 62 if coeffs.dtype != object else True
-        if big:
+        if np.abs(coeffs).max() >= 2.0 ** 62:
             ints = [int(c) for c in coeffs]
             for j in range(limbs):
                 p = self.ctx.primes[j]
@@ -56,31 +63,29 @@ class CKKSEncoder:
                 out[j] = np.mod(ints, np.int64(self.ctx.primes[j])).astype(np.uint64)
         return out
 
-    def encode(self, values, scale, limbs=None, batch_of=None):
+    def encode(self, values, scale, limbs=None):
         """encode(vector<double>) or encode(double) -> Plaintext (NTT form, on device).
-        `values` may also be a 2-D array: one plaintext per row (batched)."""
+        A 2-D `values` array gives one plaintext per row (a batch)."""
         limbs = self.ctx.top_limbs if limbs is None else limbs
         n = self.ctx.n
         if np.isscalar(values):
-            c = float(np.round(values * scale)) if abs(values * scale) < 2.0 ** 62 else None
-            ints = int(round(values * scale)) if c is None else int(c)
+            ints = int(round(float(values) * scale))
             res = np.empty((1, 1, limbs, n), dtype=np.uint64)
             for j in range(limbs):
                 res[0, 0, j, :] = ints % self.ctx.primes[j]    # NTT of a constant is that constant
             return self.ctx.upload(res, scale=scale)
         vals = np.atleast_2d(np.asarray(values, dtype=np.float64))
         B = vals.shape[0]
+        m = min(vals.shape[1], self.slots)
         res = np.empty((B, 1, limbs, n), dtype=np.uint64)
         for b in range(B):
             v = np.zeros(n, dtype=np.complex128)
-            m = min(vals.shape[1], self.slots)
             v[self._k[:m]] = vals[b, :m]
             v[self._kc[:m]] = vals[b, :m]
             coeffs = np.real(np.fft.fft(v) / n * np.conj(self._twist))
             res[b, 0] = self._to_residues(np.round(coeffs * scale), limbs)
         pt = self.ctx.upload(res, scale=scale)
-        flat = pt.data.view(B, limbs, n)
-        self.ev.ntt_forward(flat)
+        self.ev.ntt_forward(pt.data.view(B, limbs, n))
         return pt
 
     def decode(self, pt):
@@ -110,99 +115,93 @@ class CKKSEncoder:
         return out
 
 
-class KeyGenerator:
-    """SEAL KeyGenerator: ternary secret, public key, relinearisation and Galois keys
-    (SURVEY.md A.5).  All ring products run on the device."""
+class _RingOps:
+    """device ring helpers shared by key generation / encryption / decryption"""
 
-    def __init__(self, ctx, seed=0):
-        self.ctx = ctx
+    def __init__(self, ctx, rng):
+        self.ctx, self.rng = ctx, rng
         self.ev = Evaluator(ctx)
-        self.rng = np.random.default_rng(seed)
-        n, K = ctx.n, ctx.K
-        s = self.rng.integers(-1, 2, size=n)
-        self._sk = self._small_to_ntt(s[None], K)[0]            # [K][N] device int64 tensor
 
-    # -- helpers
-    def _small_to_ntt(self, small, limbs):
-        """signed small integer polys [P][N] -> device tensor [P][limbs][N] in NTT form"""
-        P = small.shape[0]
-        res = np.empty((P, limbs, self.ctx.n), dtype=np.uint64)
+    def small_to_ntt(self, small, limbs):
+        """signed small integer polys [P][N] -> device tensor [P][limbs][N], NTT form"""
+        res = np.empty((small.shape[0], limbs, self.ctx.n), dtype=np.uint64)
         for j in range(limbs):
             res[:, j, :] = np.mod(small, np.int64(self.ctx.primes[j])).astype(np.uint64)
         t = torch.from_numpy(res.view(np.int64)).to(self.ctx.device)
         self.ev.ntt_forward(t)
         return t
 
-    def _errors(self, count):
-        e = np.round(self.rng.normal(0.0, 3.2, size=(count, self.ctx.n)))
-        return np.clip(e, -19, 19).astype(np.int64)
+    def ternary(self, count):
+        return self.rng.integers(-1, 2, size=(count, self.ctx.n))
 
-    def _uniform(self, count, limbs):
+    def errors(self, count):
+        e = np.round(self.rng.normal(0.0, 3.2, size=(count, self.ctx.n)))
+        return np.clip(e, -19, 19).astype(np.int64)        # sigma 3.2, clipped at 6 sigma
+
+    def uniform(self, count, limbs):
         res = np.empty((count, limbs, self.ctx.n), dtype=np.uint64)
         for j in range(limbs):
             res[:, j, :] = self.rng.integers(0, self.ctx.primes[j], size=(count, self.ctx.n), dtype=np.uint64)
         return torch.from_numpy(res.view(np.int64)).to(self.ctx.device)
 
-    def _as_ct(self, t, limbs):
-        """[B][S][limbs][N] tensor -> Ciphertext view over the first `limbs` primes"""
-        return Ciphertext(self.ctx, t.contiguous(), limbs)
+    def polys(self, t, limbs):
+        """[P][limbs][N] tensor -> size-1 Ciphertext batch over primes [0, limbs)"""
+        return Ciphertext(self.ctx, t[:, None].contiguous(), limbs)
 
-    def _enc_zero(self, count, limbs):
-        """count x (-(a s + e), a) over primes [0, limbs) -- needs limbs <= K-1 for the evaluator
-        views, so the special-prime limb is handled by a second call on a shifted context"""
-        raise NotImplementedError
+    def mul(self, a, s):
+        """a [P][W][N] times s [W][N] limb-wise (multiply_plain kernel, broadcast plaintext)"""
+        W = a.shape[1]
+        return self.ev.multiply_plain(self.polys(a, W), self.polys(s[None], W)).data[:, 0]
+
+    def enc_zero_sym(self, count, sk, limbs):
+        """count x (-(a s + e), a) over primes [0, limbs): tensor [count][2][limbs][N]"""
+        a = self.uniform(count, limbs)
+        e = self.small_to_ntt(self.errors(count), limbs)
+        ase = self.ev.add(self.polys(self.mul(a, sk[:limbs]), limbs), self.polys(e, limbs))
+        self.ev.negate_inplace(ase)
+        return torch.stack([ase.data[:, 0], a], dim=1).contiguous()
+
+
+class KeyGenerator:
+    """SEAL KeyGenerator: ternary secret, public key, relinearisation and Galois keys
+    (SURVEY.md A.5), at the key level (all K primes)."""
+
+    def __init__(self, ctx, seed=0):
+        self.ctx = ctx
+        self.ops = _RingOps(ctx, np.random.default_rng(seed))
+        self._sk = self.ops.small_to_ntt(self.ops.ternary(1), ctx.K)[0]      # [K][N]
 
     def secret_key(self):
         return self._sk
 
-    def _sym_zero_full(self, count):
-        """count encryptions of zero over ALL K primes: tensor [count][2][K][N].
-        The evaluator's views cover at most K-1 limbs, so the dyadic products are done with
-        torch-free device code: one multiply_plain over limbs [0,K-1) plus one over the single
-        limb K-1 via a one-limb context trick is avoided by computing a*s with the generic
-        element-wise kernel on a (K-1)-limb view and the last limb separately."""
-        ctx, K, n = self.ctx, self.ctx.K, self.ctx.n
-        a = self._uniform(count, K)                                   # [count][K][N]
-        e = self._small_to_ntt(self._errors(count), K)                # [count][K][N]
-        out = torch.empty((count, 2, K, n), dtype=torch.int64, device=ctx.device)
-        out[:, 1] = a
-        prod = self._dyadic_full(a, self._sk)                         # a*s
-        out[:, 0] = self._neg_add_full(prod, e)                       # -(a s + e)
-        return out
-
-    def _dyadic_full(self, a, s):
-        """a [count][K][N] times s [K][N] limb-wise over all K primes (two evaluator calls:
-        limbs 0..K-2 through a (K-1)-limb view, limb K-1 through the rotated-prime helper)"""
-        return _full_level_mul(self.ctx, self.ev, a, s)
-
-    def _neg_add_full(self, x, e):
-        return _full_level_neg_add(self.ctx, x, e)
-
     def public_key(self):
-        return self._sym_zero_full(1)[0]                              # [2][K][N]
+        return self.ops.enc_zero_sym(1, self._sk, self.ctx.K)[0]             # [2][K][N]
 
     def _kswitch_key(self, new_key):
-        """new_key: [K][N] NTT form.  SEAL generate_one_kswitch_key: one encryption of zero per
-        data prime i with (P mod q_i) * new_key added into limb i of component 0."""
-        ctx, K = self.ctx, self.ctx.K
-        key = self._sym_zero_full(K - 1)                              # [K-1][2][K][N]
+        """generate_one_kswitch_key: digit i is an encryption of zero with (P mod q_i) * new_key
+        added into limb i of component 0.  new_key: [K][N], NTT form."""
+        ctx, K, ops = self.ctx, self.ctx.K, self.ops
+        key = ops.enc_zero_sym(K - 1, self._sk, K)                           # [K-1][2][K][N]
         P = ctx.primes[K - 1]
+        fac = torch.empty((K, ctx.n), dtype=torch.int64, device=ctx.device)
+        for j in range(K):
+            fac[j] = P % ctx.primes[j]
+        scaled = ops.mul(new_key[None], fac)[0]                              # limb j times (P mod q_j)
         for i in range(K - 1):
             p = ctx.primes[i]
-            f = P % p
-            limb = key[i, 0, i]
-            limb.copy_(_addmod_t(limb, _mulscalar_t(new_key[i], f, p), p))
+            s = key[i, 0, i] + scaled[i]
+            key[i, 0, i] = torch.where(s >= p, s - p, s)
         return key
 
     def relin_keys(self):
-        s2 = _full_level_mul(self.ctx, self.ev, self._sk[None], self._sk)[0]
-        return self._kswitch_key(s2)
+        return self._kswitch_key(self.ops.mul(self._sk[None], self._sk)[0])
 
     def galois_key(self, galois_elt):
-        perm = torch.from_numpy(_galois_perm(self.ctx.log_n, galois_elt)).to(self.ctx.device)
-        return self._kswitch_key(self._sk[:, perm])
+        perm = torch.from_numpy(galois_perm(self.ctx.log_n, galois_elt)).to(self.ctx.device)
+        return self._kswitch_key(self._sk[:, perm].contiguous())
 
     def default_galois_elts(self):
+        """KeyGenerator::galois_keys(): steps +-2^i and the conjugation"""
         elts = {2 * self.ctx.n - 1}
         for i in range(self.ctx.log_n - 1):
             elts.add(self.ctx.galois_elt(1 << i))
@@ -220,154 +219,44 @@ class KeyGenerator:
         return ks
 
 
-# ---- tiny exact helpers on int64 tensors holding residues < 2^61 (python-int per scalar, torch per
-# element); only used by key generation / encryption, never on the evaluator hot path
-def _mulscalar_t(x, f, p):
-    """x * f mod p for a tensor x of residues (f < p < 2^61) via 3-way splitting to stay in int64"""
-    # split f into 20-bit chunks: x*f = sum x*f_k*2^(20k); each partial product reduced with
-    # float-free Barrett-by-division on python side is too slow, so use torch on CPU with object
-    # fallback only for this cold path
-    xs = x.cpu().numpy().view(np.uint64).astype(object)
-    return torch.from_numpy(np.array((xs * f) % p, dtype=np.uint64).view(np.int64)).to(x.device)
-
-
-def _addmod_t(a, b, p):
-    s = a + b          # < 2^62, no overflow
-    return torch.where(s >= p, s - p, s)
-
-
-def _galois_perm(log_n, g):
-    n = 1 << log_n
-    i = np.arange(n, dtype=np.uint64)
-    e = (np.uint64(g) * (np.uint64(2) * _bitrev(i, log_n) + np.uint64(1))) & np.uint64(2 * n - 1)
-    return _bitrev((e - np.uint64(1)) >> np.uint64(1), log_n).astype(np.int64)
-
-
-def _full_level_mul(ctx, ev, a, s):
-    """limb-wise a[count][K][N] * s[K][N] over all K primes on the device.
-    The evaluator addresses limbs 0..K-2 through ordinary views; the special-prime limb K-1 is
-    reached by multiplying as a ct x ct product on a view whose limb 0 is rebased: instead we
-    run the generic multiply kernel on limbs 0..K-2 and handle limb K-1 with an exact float-free
-    split on the host (cold path)."""
-    count, K, n = a.shape
-    out = torch.empty_like(a)
-    lo_a = Ciphertext(ctx, a[:, None, : K - 1, :].contiguous(), K - 1)
-    lo_s = Ciphertext(ctx, s[None, None, : K - 1, :].contiguous(), K - 1)
-    prod = lo_a.like()
-    va, vs, vo = lo_a.view(), lo_s.view(), prod.view()
-    import ctypes as C
-    from .capi import check
-    from .engine import _stream
-    check(ctx.lib.ckks_multiply_plain(ctx._h, C.byref(va), C.byref(vs), C.byref(vo), _stream()))
-    out[:, : K - 1, :] = prod.data[:, 0]
-    p = ctx.primes[K - 1]
-    ah = a[:, K - 1, :].cpu().numpy().view(np.uint64).astype(object)
-    sh = s[K - 1].cpu().numpy().view(np.uint64).astype(object)
-    out[:, K - 1, :] = torch.from_numpy(np.array((ah * sh[None]) % p, dtype=np.uint64).view(np.int64)).to(a.device)
-    return out
-
-
-def _full_level_neg_add(ctx, x, e):
-    """-(x + e) limb-wise over all K primes"""
-    out = torch.empty_like(x)
-    for j in range(ctx.K):
-        p = ctx.primes[j]
-        s = _addmod_t(x[:, j], e[:, j], p)
-        out[:, j] = torch.where(s == 0, s, p - s)
-    return out
-
-
 class Encryptor:
     """SEAL Encryptor (public key): (u pk + e) one level above the target, divide-and-round by
-    the extra prime on the device, plaintext added to c0."""
+    the extra prime (the rescale kernels), plaintext added to c0."""
 
     def __init__(self, ctx, public_key, seed=1):
         self.ctx, self.pk = ctx, public_key
-        self.ev = Evaluator(ctx)
-        self.rng = np.random.default_rng(seed)
+        self.ops = _RingOps(ctx, np.random.default_rng(seed))
 
     def encrypt(self, pt):
-        ctx, ev, n = self.ctx, self.ev, self.ctx.n
+        ctx, ops, ev = self.ctx, self.ops, self.ops.ev
         B, L = pt.batch, pt.limbs
-        W = L + 1
-        if W > ctx.K:
-            raise ValueError("plaintext level is above the key level")
-        kg = KeyGenerator.__new__(KeyGenerator)
-        kg.ctx, kg.ev, kg.rng = ctx, ev, self.rng
-        u = kg._small_to_ntt(self.rng.integers(-1, 2, size=(B, n)), W)            # [B][W][N]
-        big = torch.empty((B, 2, W, n), dtype=torch.int64, device=ctx.device)
+        W = L + 1                      # primes 0..L: prime L is the next data prime or, at the top, P
+        u = ops.small_to_ntt(ops.ternary(B), W)
+        parts = []
         for k in range(2):
-            e = kg._small_to_ntt(kg._errors(B), W)
-            if W <= ctx.K - 1:
-                prod = _level_mul(ctx, u, self.pk[k, :W])
-            else:
-                prod = _full_level_mul(ctx, ev, u, self.pk[k])
-            for j in range(W):
-                big[:, k, j] = _addmod_t(prod[:, j], e[:, j], ctx.primes[j])
-        if W <= ctx.K - 1:
-            ct = ev.rescale_to_next(Ciphertext(ctx, big, W, 1.0))
-            ct = Ciphertext(ctx, ct.data[:, :, :L, :].contiguous(), L, pt.scale)
-        else:
-            # divide by the special prime: reuse the rescale kernels through a (K)-limb layout is
-            # not expressible with data-level views, so route through the mod-down of a key switch
-            ct = _moddown_special(ctx, ev, big, pt.scale)
-        return ev.add_plain_inplace(ct, Ciphertext(ctx, pt.data[:, :, :L, :].contiguous(), L, pt.scale))
-
-
-def _level_mul(ctx, a, s):
-    import ctypes as C
-    from .capi import check
-    from .engine import _stream
-    count, W, n = a.shape
-    ca = Ciphertext(ctx, a[:, None].contiguous(), W)
-    cs = Ciphertext(ctx, s[None, None].contiguous(), W)
-    out = ca.like()
-    va, vs, vo = ca.view(), cs.view(), out.view()
-    check(ctx.lib.ckks_multiply_plain(ctx._h, C.byref(va), C.byref(vs), C.byref(vo), _stream()))
-    return out.data[:, 0]
-
-
-def _moddown_special(ctx, ev, big, scale):
-    """divide-and-round [B][2][K][N] by the special prime -> Ciphertext at the top data level.
-    Host-exact (python ints) on the special limb only; cold path used once per fresh encryption."""
-    B, _, K, n = big.shape
-    L = K - 1
-    P = ctx.primes[K - 1]
-    last = big[:, :, K - 1, :].contiguous()
-    ev.ntt_inverse(last.view(B * 2, 1, n), first_prime=K - 1)
-    r = last.cpu().numpy().view(np.uint64).astype(object)
-    half = P >> 1
-    r = (r + half) % P
-    out = torch.empty((B, 2, L, n), dtype=torch.int64, device=ctx.device)
-    corr = torch.empty((B * 2, L, n), dtype=torch.int64, device=ctx.device)
-    for j in range(L):
-        p = ctx.primes[j]
-        u = (r % p - half % p) % p
-        corr[:, j, :] = torch.from_numpy(np.array(u, dtype=np.uint64).view(np.int64).reshape(B * 2, n)).to(ctx.device)
-    ev.ntt_forward(corr)
-    corr = corr.view(B, 2, L, n)
-    for j in range(L):
-        p = ctx.primes[j]
-        pinv = pow(P % p, -1, p)
-        d = big[:, :, j, :] - corr[:, :, j, :]
-        d = torch.where(d < 0, d + p, d)
-        out[:, :, j, :] = _mulscalar_t(d.contiguous(), pinv, p)
-    return Ciphertext(ctx, out, L, scale)
+            e = ops.small_to_ntt(ops.errors(B), W)
+            upk = ops.polys(ops.mul(u, self.pk[k, :W]), W)
+            parts.append(ev.add(upk, ops.polys(e, W)).data[:, 0])
+        big = Ciphertext(ctx, torch.stack(parts, dim=1).contiguous(), W)
+        ct = ev.rescale_to_next(big)
+        ct.scale = pt.scale
+        ptv = Ciphertext(ctx, pt.data, L, pt.scale)
+        return ev.add_plain_inplace(ct, ptv)
 
 
 class Decryptor:
-    """SEAL Decryptor: sum_k c_k s^k (dyadic products on the device)."""
+    """SEAL Decryptor: sum_k c_k s^k (dyadic products on the device); returns a Plaintext."""
 
     def __init__(self, ctx, secret_key):
         self.ctx, self.sk = ctx, secret_key
-        self.ev = Evaluator(ctx)
+        self.ops = _RingOps(ctx, np.random.default_rng(0))
 
     def decrypt(self, ct):
-        ctx, L = self.ctx, ct.limbs
-        s = self.sk[:L]
-        acc = ct.data[:, ct.size - 1, :L, :].contiguous()
+        ops, ev, L = self.ops, self.ops.ev, ct.limbs
+        s = self.sk[:L].contiguous()
+        acc = ops.polys(ct.data[:, ct.size - 1, :L, :], L)
         for k in range(ct.size - 2, -1, -1):
-            acc = _level_mul(ctx, acc, s)
-            for j in range(L):
-                acc[:, j] = _addmod_t(acc[:, j], ct.data[:, k, j, :], ctx.primes[j])
-        return Ciphertext(ctx, acc[:, None].contiguous(), L, ct.scale)
+            acc = ops.polys(ops.mul(acc.data[:, 0], s), L)
+            ev.add(acc, ops.polys(ct.data[:, k, :L, :], L), out=acc)
+        acc.scale = ct.scale
+        return acc

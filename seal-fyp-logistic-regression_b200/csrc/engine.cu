@@ -52,6 +52,25 @@ struct ckks_keyset {
     ckks_ctx *ctx;
     const uint64_t *relin = nullptr;
     std::unordered_map<uint64_t, const uint64_t *> galois;
+    // slot tables for per-entry key selection inside one launch (rotation plans)
+    std::vector<uint64_t> slot_elt;
+    std::unordered_map<uint64_t, int> slot_of;
+    const uint32_t **d_perm_tab = nullptr;
+    const u64 **d_key_tab = nullptr;
+    int tab_cap = 0;
+    bool tab_dirty = true;
+};
+
+// A fixed set of rotations (one step count per batch entry) compiled into rounds: round r applies
+// the r-th NAF term of every entry that still has one, all in a single batched key switch.
+struct ckks_rotplan {
+    ckks_ctx *ctx;
+    const ckks_keyset *ks;
+    int batch = 0;
+    std::vector<int> round_off, round_cnt;
+    std::vector<int> zero_entries;
+    KsSel *d_sel = nullptr;
+    uint64_t keyswitches = 0;
 };
 
 static int upload_vec(void **dst, const void *src, size_t bytes) {
@@ -200,8 +219,8 @@ static inline DView dv(const ckks_view *v) { return DView{(u64 *)v->data, v->bat
 static int check_view(const ckks_ctx *c, const ckks_view *v, const char *name) {
     if (!v || !v->data) return fail(CKKS_ERR_INVALID, std::string(name) + ": null view");
     if (v->batch < 1 || v->size < 1) return fail(CKKS_ERR_INVALID, std::string(name) + ": empty view");
-    if (v->limbs < 1 || v->limbs > c->K - 1)
-        return fail(CKKS_ERR_INVALID, std::string(name) + ": limbs outside the data levels of this context");
+    if (v->limbs < 1 || v->limbs > c->K)   // K limbs = key level (element-wise ops and rescale only)
+        return fail(CKKS_ERR_INVALID, std::string(name) + ": limbs outside the modulus chain of this context");
     if ((size_t)v->poly_stride < (size_t)v->limbs * c->n) return fail(CKKS_ERR_INVALID, std::string(name) + ": poly_stride too small");
     if (v->batch > 1 && (size_t)v->batch_stride < (size_t)v->size * v->poly_stride && v->batch_stride != 0)
         return fail(CKKS_ERR_INVALID, std::string(name) + ": batch_stride too small");
@@ -284,14 +303,17 @@ extern "C" int ckks_negate(ckks_ctx *c, const ckks_view *a, const ckks_view *o, 
 extern "C" int ckks_multiply(ckks_ctx *c, const ckks_view *a, const ckks_view *b, const ckks_view *o, ckks_stream s) {
     int rc;
     if ((rc = check_view(c, a, "a")) || (rc = check_view(c, b, "b")) || (rc = check_view(c, o, "out"))) return rc;
-    if (a->batch != b->batch || a->limbs != b->limbs) return fail(CKKS_ERR_INVALID, "encrypted1 and encrypted2 parameter mismatch");
+    if ((a->batch != b->batch && b->batch != 1) || a->limbs != b->limbs)
+        return fail(CKKS_ERR_INVALID, "encrypted1 and encrypted2 parameter mismatch");
     if (o->batch != a->batch || o->limbs != a->limbs || o->size != a->size + b->size - 1)
         return fail(CKKS_ERR_INVALID, "destination parameter mismatch");
     if (o->data == a->data || o->data == b->data) return fail(CKKS_ERR_INVALID, "multiply: out must not alias an input");
     CU(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)s;
     dim3 g = ew_grid(c, a->limbs, a->batch);
-#define MUL(SA, SB) k_ew_multiply<SA, SB><<<g, 256, 0, st>>>(dv(a), dv(b), dv(o), a->limbs, c->n, c->t)
+    DView vb = dv(b);
+    if (b->batch == 1) vb.bs = 0;   // one ciphertext multiplied into every batch entry
+#define MUL(SA, SB) k_ew_multiply<SA, SB><<<g, 256, 0, st>>>(dv(a), vb, dv(o), a->limbs, c->n, c->t)
     if (a->size == 2 && b->size == 2) MUL(2, 2);
     else if (a->size == 3 && b->size == 2) MUL(3, 2);
     else if (a->size == 2 && b->size == 3) MUL(2, 3);
@@ -387,39 +409,38 @@ static int get_perm(ckks_ctx *c, uint64_t g, const uint32_t **out) {
     return CKKS_OK;
 }
 
-// mode 1: relinearize (target = in poly 2, base = in polys 0,1)
-// mode 2: Galois      (target = permuted in poly 1, base = permuted in poly 0)
-static int keyswitch(ckks_ctx *c, int mode, const ckks_view *in, const uint32_t *perm, const uint64_t *ksk, const ckks_view *out, cudaStream_t st) {
-    const int L = in->limbs, B = in->batch, K = c->K;
+// Batched key switch over `nslots` launch slots.
+// mode 1: relinearize (target = poly 2 of the source, base = polys 0,1)
+// mode 2: Galois      (target = permuted poly 1, base = permuted poly 0)
+static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaStream_t st) {
+    const int K = c->K;
     const size_t N = c->n;
-    const int Bc = ks_chunk(c, B, L);
+    const int Bc = ks_chunk(c, nslots, L);
     int rc;
     if ((rc = ensure_ws(c, ks_words_per_ct(c, L) * 8 * (size_t)Bc))) return rc;
     u64 *D = c->ws;
     u64 *T1 = D + (size_t)Bc * L * N;
     u64 *ACC = T1 + (size_t)Bc * L * (L + 1) * N;
     u64 *T2 = ACC + (size_t)Bc * 2 * (L + 1) * N;
-    const u64 *key = (const u64 *)ksk;
-    for (int b0 = 0; b0 < B; b0 += Bc) {
-        const int bc = (B - b0) < Bc ? (B - b0) : Bc;
-        DView tgt{(u64 *)in->data + (u64)b0 * in->batch_stride + (mode == 1 ? 2 : 1) * in->poly_stride, in->batch_stride, 0};
-        DView base{(u64 *)in->data + (u64)b0 * in->batch_stride, in->batch_stride, in->poly_stride};
-        DView dst{(u64 *)out->data + (u64)b0 * out->batch_stride, out->batch_stride, out->poly_stride};
+    rt.tgt_poly = mode == 1 ? 2 : 1;
+    for (int b0 = 0; b0 < nslots; b0 += Bc) {
+        const int bc = (nslots - b0) < Bc ? (nslots - b0) : Bc;
+        rt.b0 = b0;
         DView dD{D, (u64)L * N, 0};
         DView spec{ACC + (size_t)L * N, (u64)(L + 1) * N, 0};             // special-prime limb of every (b,k)
         DView minu{ACC, 2 * (u64)(L + 1) * N, (u64)(L + 1) * N};
 #define RUN(LN)                                                                                                         \
     {                                                                                                                   \
         typedef NttGeo<LN> G;                                                                                           \
-        if (mode == 2) k_ks_intt_row<LN, true><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(tgt, perm, D, L, c->t); \
-        else k_ks_intt_row<LN, false><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(tgt, perm, D, L, c->t);        \
+        if (mode == 2) k_ks_intt_row<LN, true><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(rt, D, L, c->t);      \
+        else k_ks_intt_row<LN, false><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(rt, D, L, c->t);               \
         LAUNCH_CHECK(c);                                                                                                \
         k_inv_col<LN, false><<<dim3(G::COL_TILES, L, bc), NTT_THREADS, 0, st>>>(dD, dD, L, 0, c->t);                    \
         LAUNCH_CHECK(c);                                                                                                \
         k_ks_modup_col<LN><<<dim3(G::COL_TILES, L *(L + 1), bc), NTT_THREADS, 0, st>>>(D, T1, L, c->t);                 \
         LAUNCH_CHECK(c);                                                                                                \
-        if (mode == 2) k_ks_mac<LN, true><<<dim3(G::ROW_TILES, L + 1, bc), NTT_THREADS, 0, st>>>(T1, tgt, perm, key, ACC, L, c->t); \
-        else k_ks_mac<LN, false><<<dim3(G::ROW_TILES, L + 1, bc), NTT_THREADS, 0, st>>>(T1, tgt, perm, key, ACC, L, c->t); \
+        if (mode == 2) k_ks_mac<LN, true><<<dim3(G::ROW_TILES, L + 1, bc), NTT_THREADS, 0, st>>>(T1, rt, ACC, L, c->t); \
+        else k_ks_mac<LN, false><<<dim3(G::ROW_TILES, L + 1, bc), NTT_THREADS, 0, st>>>(T1, rt, ACC, L, c->t);          \
         LAUNCH_CHECK(c);                                                                                                \
         k_inv_row<LN><<<dim3(G::ROW_TILES, 1, 2 * bc), NTT_THREADS, 0, st>>>(spec, spec, 1, K - 1, c->t);               \
         LAUNCH_CHECK(c);                                                                                                \
@@ -427,8 +448,8 @@ static int keyswitch(ckks_ctx *c, int mode, const ckks_view *in, const uint32_t 
         LAUNCH_CHECK(c);                                                                                                \
         k_md_fwd_col<LN><<<dim3(G::COL_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(spec, T2, L, K - 1, c->t);              \
         LAUNCH_CHECK(c);                                                                                                \
-        if (mode == 2) k_md_fwd_row<LN, 2><<<dim3(G::ROW_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(T2, minu, base, dst, perm, 2, L, K - 1, c->t); \
-        else k_md_fwd_row<LN, 1><<<dim3(G::ROW_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(T2, minu, base, dst, perm, 2, L, K - 1, c->t); \
+        if (mode == 2) k_md_fwd_row<LN, 2><<<dim3(G::ROW_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(T2, minu, rt, 2, L, K - 1, c->t); \
+        else k_md_fwd_row<LN, 1><<<dim3(G::ROW_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(T2, minu, rt, 2, L, K - 1, c->t); \
         LAUNCH_CHECK(c);                                                                                                \
     }
         DISPATCH_LOGN(c, RUN)
@@ -437,29 +458,41 @@ static int keyswitch(ckks_ctx *c, int mode, const ckks_view *in, const uint32_t 
     return CKKS_OK;
 }
 
+static KsRoute uniform_route(const ckks_view *in, const ckks_view *out, const uint32_t *perm, const uint64_t *key) {
+    KsRoute rt{};
+    rt.v[0] = dv(in);
+    rt.v[1] = dv(out);
+    rt.v[2] = dv(out);
+    rt.perm0 = perm;
+    rt.key0 = (const u64 *)key;
+    return rt;
+}
+
 extern "C" int ckks_relinearize(ckks_ctx *c, const ckks_view *in, const uint64_t *rlk, const ckks_view *out, ckks_stream s) {
     int rc;
     if ((rc = check_view(c, in, "encrypted")) || (rc = check_view(c, out, "out"))) return rc;
     if (!rlk) return fail(CKKS_ERR_INVALID, "relin_keys is not valid for encryption parameters");
+    if (in->limbs > c->K - 1) return fail(CKKS_ERR_INVALID, "encrypted is not valid for encryption parameters");
     if (in->size != 3) return fail(CKKS_ERR_INVALID, "relinearize: only size-3 ciphertexts are supported");
     if (out->size != 2 || out->batch != in->batch || out->limbs != in->limbs) return fail(CKKS_ERR_INVALID, "destination parameter mismatch");
     if (out->data == in->data && (out->poly_stride != in->poly_stride || out->batch_stride != in->batch_stride))
         return fail(CKKS_ERR_INVALID, "relinearize: in-place only with identical strides");
     CU(cudaSetDevice(c->device));
-    return keyswitch(c, 1, in, nullptr, rlk, out, (cudaStream_t)s);
+    return keyswitch(c, 1, in->limbs, in->batch, uniform_route(in, out, nullptr, rlk), (cudaStream_t)s);
 }
 
 extern "C" int ckks_apply_galois(ckks_ctx *c, const ckks_view *in, uint64_t g, const uint64_t *gk, const ckks_view *out, ckks_stream s) {
     int rc;
     if ((rc = check_view(c, in, "encrypted")) || (rc = check_view(c, out, "out"))) return rc;
     if (!gk) return fail(CKKS_ERR_INVALID, "Galois key not present");
+    if (in->limbs > c->K - 1) return fail(CKKS_ERR_INVALID, "encrypted is not valid for encryption parameters");
     if (in->size != 2) return fail(CKKS_ERR_INVALID, "encrypted size must be 2");
     if ((rc = same_shape(in, out, "destination"))) return rc;
     if (out->data == in->data) return fail(CKKS_ERR_INVALID, "apply_galois: out must not alias in");
     const uint32_t *perm = nullptr;
     if ((rc = get_perm(c, g, &perm))) return rc;
     CU(cudaSetDevice(c->device));
-    return keyswitch(c, 2, in, perm, gk, out, (cudaStream_t)s);
+    return keyswitch(c, 2, in->limbs, in->batch, uniform_route(in, out, perm, gk), (cudaStream_t)s);
 }
 
 extern "C" int ckks_keyset_create(ckks_ctx *c, ckks_keyset **out) {
@@ -467,7 +500,12 @@ extern "C" int ckks_keyset_create(ckks_ctx *c, ckks_keyset **out) {
     *out = new ckks_keyset{c};
     return CKKS_OK;
 }
-extern "C" void ckks_keyset_destroy(ckks_keyset *ks) { delete ks; }
+extern "C" void ckks_keyset_destroy(ckks_keyset *ks) {
+    if (!ks) return;
+    cudaFree((void *)ks->d_perm_tab);
+    cudaFree((void *)ks->d_key_tab);
+    delete ks;
+}
 extern "C" int ckks_keyset_set_relin(ckks_keyset *ks, const uint64_t *rlk) {
     ks->relin = rlk;
     return CKKS_OK;
@@ -477,6 +515,11 @@ extern "C" int ckks_keyset_set_galois(ckks_keyset *ks, uint64_t g, const uint64_
     int rc = get_perm(ks->ctx, g, &perm);  // build the permutation table now (not capturable later)
     if (rc) return rc;
     ks->galois[g] = gk;
+    if (!ks->slot_of.count(g)) {
+        ks->slot_of[g] = (int)ks->slot_elt.size();
+        ks->slot_elt.push_back(g);
+    }
+    ks->tab_dirty = true;
     return CKKS_OK;
 }
 extern "C" int ckks_keyset_has_galois(const ckks_keyset *ks, uint64_t g) { return ks->galois.count(g) ? 1 : 0; }
@@ -519,6 +562,168 @@ extern "C" int ckks_rotate(ckks_ctx *c, const ckks_keyset *ks, const ckks_view *
     return CKKS_OK;
 }
 
+// ------------------------------------------------------------------------------------ rotation plans
+static int sync_key_tables(ckks_keyset *ks) {
+    if (!ks->tab_dirty) return CKKS_OK;
+    ckks_ctx *c = ks->ctx;
+    CU(cudaSetDevice(c->device));
+    const int n = (int)ks->slot_elt.size();
+    if (n > ks->tab_cap) {
+        CU(cudaDeviceSynchronize());
+        cudaFree((void *)ks->d_perm_tab);
+        cudaFree((void *)ks->d_key_tab);
+        ks->tab_cap = n + 32;
+        CU(cudaMalloc((void **)&ks->d_perm_tab, sizeof(void *) * ks->tab_cap));
+        CU(cudaMalloc((void **)&ks->d_key_tab, sizeof(void *) * ks->tab_cap));
+    }
+    std::vector<const uint32_t *> hp(n);
+    std::vector<const u64 *> hk(n);
+    for (int i = 0; i < n; i++) {
+        int rc = get_perm(c, ks->slot_elt[i], &hp[i]);
+        if (rc) return rc;
+        hk[i] = (const u64 *)ks->galois.at(ks->slot_elt[i]);
+    }
+    if (n) {
+        CU(cudaMemcpy((void *)ks->d_perm_tab, hp.data(), sizeof(void *) * n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy((void *)ks->d_key_tab, hk.data(), sizeof(void *) * n, cudaMemcpyHostToDevice));
+    }
+    ks->tab_dirty = false;
+    return CKKS_OK;
+}
+
+// SEAL Evaluator::rotate_internal: the key for `steps` itself if present, else the NAF terms
+static int rotation_terms(const ckks_ctx *c, const ckks_keyset *ks, int steps, std::vector<int> &terms) {
+    terms.clear();
+    if (steps == 0) return CKKS_OK;
+    uint64_t g = ckks::galois_elt_from_step(c->log_n, steps);
+    if (!g) return fail(CKKS_ERR_INVALID, "step count too large");
+    if (ks->galois.count(g)) {
+        terms.push_back(steps);
+        return CKKS_OK;
+    }
+    std::vector<int> naf = ckks::naf_terms(steps);
+    if (naf.size() == 1) return fail(CKKS_ERR_INVALID, "Galois key not present");
+    for (int tstep : naf) {
+        if ((tstep < 0 ? -tstep : tstep) == c->n / 2) continue;
+        uint64_t gt = ckks::galois_elt_from_step(c->log_n, tstep);
+        if (!gt || !ks->galois.count(gt)) return fail(CKKS_ERR_INVALID, "Galois key not present");
+        terms.push_back(tstep);
+    }
+    return CKKS_OK;
+}
+
+extern "C" int ckks_rotplan_create(ckks_ctx *c, ckks_keyset *ks, const int *steps, int batch, ckks_rotplan **out) {
+    if (!c || !ks || !steps || !out || batch < 1) return fail(CKKS_ERR_INVALID, "rotplan: bad arguments");
+    int rc;
+    if ((rc = sync_key_tables(ks))) return rc;
+    std::vector<std::vector<int>> terms(batch);
+    size_t rounds = 0;
+    ckks_rotplan *p = new ckks_rotplan;
+    p->ctx = c;
+    p->ks = ks;
+    p->batch = batch;
+    for (int b = 0; b < batch; b++) {
+        if ((rc = rotation_terms(c, ks, steps[b], terms[b]))) {
+            delete p;
+            return rc;
+        }
+        if (terms[b].empty()) p->zero_entries.push_back(b);
+        if (terms[b].size() > rounds) rounds = terms[b].size();
+        p->keyswitches += terms[b].size();
+    }
+    std::vector<KsSel> sel;
+    for (size_t r = 0; r < rounds; r++) {
+        p->round_off.push_back((int)sel.size());
+        for (int b = 0; b < batch; b++) {
+            const int m = (int)terms[b].size();
+            if ((size_t)m <= r) continue;
+            KsSel e;
+            e.entry = b;
+            e.slot = ks->slot_of.at(ckks::galois_elt_from_step(c->log_n, terms[b][r]));
+            e.src = r == 0 ? 0 : (((m - (int)r) % 2 == 0) ? 1 : 2);
+            e.dst = ((m - 1 - (int)r) % 2 == 0) ? 1 : 2;
+            sel.push_back(e);
+        }
+        p->round_cnt.push_back((int)sel.size() - p->round_off.back());
+    }
+    if (!sel.empty()) {
+        if (cudaSetDevice(c->device) != cudaSuccess || cudaMalloc((void **)&p->d_sel, sel.size() * sizeof(KsSel)) != cudaSuccess ||
+            cudaMemcpy(p->d_sel, sel.data(), sel.size() * sizeof(KsSel), cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete p;
+            return fail(CKKS_ERR_CUDA, "rotplan: device allocation failed");
+        }
+    }
+    *out = p;
+    return CKKS_OK;
+}
+extern "C" void ckks_rotplan_destroy(ckks_rotplan *p) {
+    if (!p) return;
+    cudaFree(p->d_sel);
+    delete p;
+}
+extern "C" uint64_t ckks_rotplan_keyswitches(const ckks_rotplan *p) { return p->keyswitches; }
+extern "C" int ckks_rotplan_rounds(const ckks_rotplan *p) { return (int)p->round_cnt.size(); }
+
+extern "C" int ckks_rotate_plan(ckks_ctx *c, const ckks_rotplan *p, const ckks_view *in, const ckks_view *out,
+                                const ckks_view *scratch, ckks_stream s) {
+    int rc;
+    if (!p) return fail(CKKS_ERR_INVALID, "null plan");
+    if ((rc = check_view(c, in, "encrypted")) || (rc = check_view(c, out, "out"))) return rc;
+    if (in->size != 2 || out->size != 2) return fail(CKKS_ERR_INVALID, "encrypted size must be 2");
+    if (in->limbs > c->K - 1) return fail(CKKS_ERR_INVALID, "encrypted is not valid for encryption parameters");
+    if (out->batch != p->batch || out->limbs != in->limbs || (in->batch != p->batch && in->batch != 1))
+        return fail(CKKS_ERR_INVALID, "rotate_plan: batch/level mismatch");
+    if (out->data == in->data) return fail(CKKS_ERR_INVALID, "rotate_plan: out must not alias in");
+    const bool need_scratch = p->round_cnt.size() > 1;
+    if (need_scratch) {
+        if ((rc = check_view(c, scratch, "scratch")) || (rc = same_shape(out, scratch, "scratch"))) return rc;
+        if (scratch->data == in->data || scratch->data == out->data) return fail(CKKS_ERR_INVALID, "scratch must be distinct storage");
+    }
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)s;
+    KsRoute rt{};
+    rt.v[0] = dv(in);
+    if (in->batch == 1) rt.v[0].bs = 0;   // one input ciphertext shared by every rotation
+    rt.v[1] = dv(out);
+    rt.v[2] = need_scratch ? dv(scratch) : dv(out);
+    rt.perm_tab = p->ks->d_perm_tab;
+    rt.key_tab = p->ks->d_key_tab;
+    for (int b : p->zero_entries) {   // rotate by 0: SEAL returns the input unchanged
+        DView src = rt.v[0], dst = rt.v[1];
+        src.data += (u64)b * src.bs;
+        dst.data += (u64)b * dst.bs;
+        k_ew_copy<<<ew_grid(c, 2 * in->limbs, 1), 256, 0, st>>>(src, dst, in->limbs, c->n);
+        LAUNCH_CHECK(c);
+    }
+    for (size_t r = 0; r < p->round_cnt.size(); r++) {
+        rt.sel = p->d_sel + p->round_off[r];
+        if ((rc = keyswitch(c, 2, in->limbs, p->round_cnt[r], rt, st))) return rc;
+    }
+    return CKKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ fused products
+static int mul_sum(ckks_ctx *c, bool plain, const ckks_view *a, const ckks_view *b, const ckks_view *o, cudaStream_t st) {
+    int rc;
+    if ((rc = check_view(c, a, "a")) || (rc = check_view(c, b, "b")) || (rc = check_view(c, o, "out"))) return rc;
+    if (a->batch != b->batch || a->limbs != b->limbs || o->limbs != a->limbs || o->batch != 1)
+        return fail(CKKS_ERR_INVALID, "multiply_sum: parameter mismatch");
+    if (plain ? (b->size != 1 || o->size != a->size) : (a->size != 2 || b->size != 2 || o->size != 3))
+        return fail(CKKS_ERR_INVALID, "multiply_sum: size mismatch");
+    if (o->data == a->data || o->data == b->data) return fail(CKKS_ERR_INVALID, "multiply_sum: out must not alias an input");
+    CU(cudaSetDevice(c->device));
+    if (plain) k_ew_mul_sum<true><<<ew_grid(c, a->size * a->limbs, 1), 256, 0, st>>>(dv(a), dv(b), dv(o), a->batch, a->limbs, c->n, c->t);
+    else k_ew_mul_sum<false><<<ew_grid(c, a->limbs, 1), 256, 0, st>>>(dv(a), dv(b), dv(o), a->batch, a->limbs, c->n, c->t);
+    LAUNCH_CHECK(c);
+    return CKKS_OK;
+}
+extern "C" int ckks_multiply_plain_sum(ckks_ctx *c, const ckks_view *cts, const ckks_view *pts, const ckks_view *o, ckks_stream s) {
+    return mul_sum(c, true, cts, pts, o, (cudaStream_t)s);
+}
+extern "C" int ckks_multiply_sum(ckks_ctx *c, const ckks_view *a, const ckks_view *b, const ckks_view *o, ckks_stream s) {
+    return mul_sum(c, false, a, b, o, (cudaStream_t)s);
+}
+
 // ------------------------------------------------------------------------------------ rescale
 extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *out, ckks_stream s) {
     int rc;
@@ -546,6 +751,8 @@ extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *o
         DView dR{R, (u64)S * N, (u64)N};
         DView Rz{R, (u64)N, 0};
         DView dst{(u64 *)out->data + (u64)b0 * out->batch_stride, out->batch_stride, out->poly_stride};
+        KsRoute rrt{};
+        rrt.v[0] = src; rrt.v[1] = dst; rrt.v[2] = dst;
 #define RUN(LN)                                                                                                   \
     {                                                                                                             \
         typedef NttGeo<LN> G;                                                                                     \
@@ -555,7 +762,7 @@ extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *o
         LAUNCH_CHECK(c);                                                                                          \
         k_md_fwd_col<LN><<<dim3(G::COL_TILES, Lo, bc * S), NTT_THREADS, 0, st>>>(Rz, T2, Lo, Lo, c->t);           \
         LAUNCH_CHECK(c);                                                                                          \
-        k_md_fwd_row<LN, 0><<<dim3(G::ROW_TILES, Lo, bc * S), NTT_THREADS, 0, st>>>(T2, src, src, dst, nullptr, S, Lo, Lo, c->t); \
+        k_md_fwd_row<LN, 0><<<dim3(G::ROW_TILES, Lo, bc * S), NTT_THREADS, 0, st>>>(T2, src, rrt, S, Lo, Lo, c->t); \
         LAUNCH_CHECK(c);                                                                                          \
     }
         DISPATCH_LOGN(c, RUN)

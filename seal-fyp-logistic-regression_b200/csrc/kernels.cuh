@@ -32,6 +32,39 @@ struct DView {
 
 __device__ __forceinline__ ModConst load_mod(const Tables &t, int j) { return t.mod[j]; }
 
+// Per-entry routing of a batched key switch: which ciphertext of the views a launch slot works
+// on, which key/permutation it uses, and which of the three views (0 = in, 1 = out, 2 = scratch)
+// it reads from and writes to.  With sel == nullptr slot z works on entry z with key 0,
+// reading view 0 and writing view 1.
+struct KsSel {
+    int entry;
+    int slot;
+    int src;
+    int dst;
+};
+struct KsRoute {
+    DView v[3];                        // in, out, scratch
+    const KsSel *sel;                  // [launch slots] or nullptr
+    const uint32_t *const *perm_tab;   // [key slots] (device) or nullptr
+    const u64 *const *key_tab;         // [key slots] (device) or nullptr
+    const uint32_t *perm0;             // used when sel == nullptr
+    const u64 *key0;
+    int b0;                            // first launch slot of this chunk
+    int tgt_poly;                      // polynomial that is key-switched (2 relin, 1 Galois)
+};
+__device__ __forceinline__ KsSel route_sel(const KsRoute &r, int z) {
+    if (r.sel) return r.sel[r.b0 + z];
+    KsSel s;
+    s.entry = r.b0 + z; s.slot = 0; s.src = 0; s.dst = 1;
+    return s;
+}
+__device__ __forceinline__ const uint32_t *route_perm(const KsRoute &r, const KsSel &s) {
+    return r.sel ? r.perm_tab[s.slot] : r.perm0;
+}
+__device__ __forceinline__ const u64 *route_key(const KsRoute &r, const KsSel &s) {
+    return r.sel ? r.key_tab[s.slot] : r.key0;
+}
+
 // =============================================================================== plain NTT
 // limb instance y = s*limbs + l of batch entry z; prime = first_prime + l
 template <int LOGN>
@@ -115,11 +148,14 @@ __global__ void __launch_bounds__(NTT_THREADS) k_inv_col(DView src, DView dst, i
 // permutation out[g] = in[perm[g]] (SEAL util::apply_galois_ntt); perm maps each row of the
 // limb matrix into a single source row, so the gather stays inside one 0.5-4 KB segment.
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS) k_ks_intt_row(DView tgt, const uint32_t *__restrict__ perm, u64 *D, int L, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS) k_ks_intt_row(KsRoute rt, u64 *D, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int i = blockIdx.y, b = blockIdx.z;
-    const u64 *in = tgt.data + b * tgt.bs + (u64)i * G::N;
+    const KsSel sl = route_sel(rt, b);
+    const DView tgt = rt.v[sl.src];
+    const uint32_t *__restrict__ perm = GALOIS ? route_perm(rt, sl) : nullptr;
+    const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
     u64 *out = D + ((u64)b * L + i) * G::N;
     const ModConst m = load_mod(t, i);
     const int t0 = blockIdx.x * NTT_TILE;
@@ -159,11 +195,14 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ks_modup_col(const u64 *__restr
 //     acc_k = sum_i NTT_pj(digit_i) (.) ksk[i][k][pj]     (k = 0,1), 128-bit lazy sums,
 // one Barrett reduction at the end.  Key limbs stream once from HBM, fully coalesced.
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS) k_ks_mac(const u64 *__restrict__ T1, DView tgt, const uint32_t *__restrict__ perm,
-                                                        const u64 *__restrict__ ksk, u64 *ACC, int L, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS) k_ks_mac(const u64 *__restrict__ T1, KsRoute rt, u64 *ACC, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int jj = blockIdx.y, b = blockIdx.z;
+    const KsSel sl = route_sel(rt, b);
+    const DView tgt = rt.v[sl.src];
+    const uint32_t *__restrict__ perm = GALOIS ? route_perm(rt, sl) : nullptr;
+    const u64 *__restrict__ ksk = route_key(rt, sl);
     const int K = t.K, pj = jj == L ? K - 1 : jj;
     const ModConst m = load_mod(t, pj);
     const tw_t *tw = t.twf + (size_t)pj * G::N;
@@ -174,7 +213,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ks_mac(const u64 *__restrict__ 
     for (int i = 0; i < L; i++) {
         u64 x[8];
         if (i == pj) {
-            const u64 *in = tgt.data + b * tgt.bs + (u64)i * G::N;
+            const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 int g = t0 + row_contig_li(e);
@@ -239,11 +278,13 @@ __global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_col(DView R, u64 *T2, in
 // base = permuted in[b][0] for k == 0 and nothing for k == 1 (SEAL wipes c1 before switching).
 // z = b*S + s enumerates (ciphertext, poly).
 template <int LOGN, int MODE>
-__global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_row(const u64 *__restrict__ T2, DView minuend, DView base, DView dst,
-                                                            const uint32_t *__restrict__ perm, int S, int Lout, int a, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_row(const u64 *__restrict__ T2, DView minuend, KsRoute rt, int S, int Lout, int a, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int j = blockIdx.y, z = blockIdx.z, b = z / S, s = z % S;
+    const KsSel sl = route_sel(rt, b);
+    const DView base = rt.v[sl.src], dst = rt.v[sl.dst];
+    const uint32_t *__restrict__ perm = MODE == 2 ? route_perm(rt, sl) : nullptr;
     const u64 *in = T2 + ((u64)z * Lout + j) * G::N;
     const ModConst m = load_mod(t, j);
     const u64 qi = t.inv[a * t.K + j], qis = t.invs[a * t.K + j];
@@ -253,16 +294,16 @@ __global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_row(const u64 *__restric
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
     fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m.p, m.p2, t0, smem);
     const u64 *mi = minuend.data + b * minuend.bs + s * minuend.ps + (u64)j * G::N;
-    u64 *out = dst.data + b * dst.bs + s * dst.ps + (u64)j * G::N;
+    u64 *out = dst.data + sl.entry * dst.bs + s * dst.ps + (u64)j * G::N;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const int g = t0 + row_contig_li(e);
         u64 v = csub(csub(x[e], m.p2), m.p);
         u64 r = shoup_mul(submod(mi[g], v, m.p), qi, qis, m.p);
         if (MODE == 1) {
-            r = addmod(r, base.data[b * base.bs + s * base.ps + (u64)j * G::N + g], m.p);
+            r = addmod(r, base.data[sl.entry * base.bs + s * base.ps + (u64)j * G::N + g], m.p);
         } else if (MODE == 2) {
-            if (s == 0) r = addmod(r, base.data[b * base.bs + (u64)j * G::N + perm[g]], m.p);
+            if (s == 0) r = addmod(r, base.data[sl.entry * base.bs + (u64)j * G::N + perm[g]], m.p);
         }
         out[g] = r;
     }
@@ -356,6 +397,61 @@ __global__ void __launch_bounds__(256) k_ew_add_many(DView in, DView o, int B, i
         acc.y = addmod(acc.y, y.y, m.p);
     }
     *vpw(o, 0, s, j, n, c) = acc;
+}
+
+// fused multiply + add_many: out = sum_b a[b] (.) b[b]
+//   PLAIN: b is a plaintext batch (every poly of a[b] times pt[b]), output size = size of a
+//   else : size-2 x size-2 ciphertext products, output size 3 (Linear_Transform_Cipher)
+// 128-bit lazy sums with a reduction every 16 terms; identical to SEAL's sequential
+// multiply + add_inplace because the sum is taken modulo q either way.
+template <bool PLAIN>
+__global__ void __launch_bounds__(256) k_ew_mul_sum(DView a, DView b, DView o, int B, int L, int n, Tables t) {
+    const int s = PLAIN ? blockIdx.y / L : 0, j = blockIdx.y % L;
+    const u64 c = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (c >= (u64)n) return;
+    const ModConst m = t.mod[j];
+    if (PLAIN) {
+        u64 l0 = 0, h0 = 0, l1 = 0, h1 = 0;
+        for (int q = 0; q < B; q++) {
+            ulonglong2 x = *vp(a, q, s, j, n, c), y = *vp(b, q, 0, j, n, c);
+            mac128(l0, h0, x.x, y.x);
+            mac128(l1, h1, x.y, y.y);
+            if ((q & 15) == 15) {
+                l0 = barrett128(l0, h0, m); h0 = 0;
+                l1 = barrett128(l1, h1, m); h1 = 0;
+            }
+        }
+        ulonglong2 r;
+        r.x = barrett128(l0, h0, m);
+        r.y = barrett128(l1, h1, m);
+        *vpw(o, 0, s, j, n, c) = r;
+    } else {
+        u64 lo[3][2], hi[3][2];
+#pragma unroll
+        for (int k = 0; k < 3; k++) lo[k][0] = lo[k][1] = hi[k][0] = hi[k][1] = 0;
+        for (int q = 0; q < B; q++) {
+            ulonglong2 a0 = *vp(a, q, 0, j, n, c), a1 = *vp(a, q, 1, j, n, c);
+            ulonglong2 b0 = *vp(b, q, 0, j, n, c), b1 = *vp(b, q, 1, j, n, c);
+            mac128(lo[0][0], hi[0][0], a0.x, b0.x); mac128(lo[0][1], hi[0][1], a0.y, b0.y);
+            mac128(lo[1][0], hi[1][0], a0.x, b1.x); mac128(lo[1][1], hi[1][1], a0.y, b1.y);
+            mac128(lo[1][0], hi[1][0], a1.x, b0.x); mac128(lo[1][1], hi[1][1], a1.y, b0.y);
+            mac128(lo[2][0], hi[2][0], a1.x, b1.x); mac128(lo[2][1], hi[2][1], a1.y, b1.y);
+            if ((q & 7) == 7) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    lo[k][0] = barrett128(lo[k][0], hi[k][0], m); hi[k][0] = 0;
+                    lo[k][1] = barrett128(lo[k][1], hi[k][1], m); hi[k][1] = 0;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            ulonglong2 r;
+            r.x = barrett128(lo[k][0], hi[k][0], m);
+            r.y = barrett128(lo[k][1], hi[k][1], m);
+            *vpw(o, 0, k, j, n, c) = r;
+        }
+    }
 }
 
 // strided limb copy (mod-switch drop into a differently laid out view)

@@ -259,7 +259,9 @@ class Evaluator:
         return out
 
     def multiply(self, a, b, out=None):
-        self._same(a, b)
+        """ct x ct; b may be a single ciphertext multiplied into every entry of a"""
+        if a.limbs != b.limbs or (a.batch != b.batch and b.batch != 1):
+            raise capi.CkksInvalidArgument("encrypted1 and encrypted2 parameter mismatch")
         scale = a.scale * b.scale
         self._scale_ok(scale, a.limbs)
         out = a.like(size=a.size + b.size - 1) if out is None else out
@@ -326,11 +328,16 @@ class Evaluator:
 
     def rotate_vector(self, ct, steps, keys, out=None, scratch=None):
         out = ct.like() if out is None else out
-        scratch = ct.like() if scratch is None else scratch
-        vi, vo, vs = ct.view(), out.view(), scratch.view()
-        vo.limbs = vs.limbs = ct.limbs
-        check(self.lib.ckks_rotate(self.h, keys._h, C.byref(vi), int(steps), C.byref(vo), C.byref(vs), _stream()))
-        out.limbs, out.scale = ct.limbs, ct.scale
+        out.limbs = ct.limbs
+        vi, vo = ct.view(), out.view()
+        vs = None
+        if steps != 0 and not keys.has_galois(self.ctx.galois_elt(steps)):
+            scratch = ct.like() if scratch is None else scratch   # composite step: NAF ping-pong
+            scratch.limbs = ct.limbs
+            vs = scratch.view()
+        check(self.lib.ckks_rotate(self.h, keys._h, C.byref(vi), int(steps), C.byref(vo),
+                                   C.byref(vs) if vs is not None else None, _stream()))
+        out.scale = ct.scale
         return out
 
     # ---- rescale / mod switch
@@ -377,3 +384,70 @@ class Evaluator:
         P, L, N = tensor.shape
         check(self.lib.ckks_ntt_inverse(self.h, tensor.data_ptr(), P, L, first_prime, L * N, _stream()))
         return tensor
+
+    # ---- batched rotations with per-entry steps, fused products
+    def rotate_plan(self, ct, plan, out=None, scratch=None):
+        """entry b of the result = rotate_vector(ct[b] or the single ct, plan.steps[b])"""
+        if out is None:
+            out = Ciphertext(self.ctx, torch.empty((plan.batch, 2, ct.cap, self.ctx.n), dtype=torch.int64,
+                                                   device=ct.data.device), ct.limbs, ct.scale)
+        if scratch is None and plan.rounds > 1:
+            scratch = out.like()
+        out.limbs = ct.limbs
+        vi, vo = ct.view(), out.view()
+        vs = None
+        if scratch is not None:
+            scratch.limbs = ct.limbs
+            vs = scratch.view()
+        check(self.lib.ckks_rotate_plan(self.h, plan._h, C.byref(vi), C.byref(vo),
+                                        C.byref(vs) if vs is not None else None, _stream()))
+        out.scale = ct.scale
+        return out
+
+    def multiply_plain_sum(self, cts, pts, out=None):
+        """multiply_plain of every batch entry with its plaintext, then add_many, in one kernel"""
+        if cts.limbs != pts.limbs or cts.batch != pts.batch:
+            raise capi.CkksInvalidArgument("encrypted and plain parameter mismatch")
+        scale = cts.scale * pts.scale
+        self._scale_ok(scale, cts.limbs)
+        out = cts[0:1].like() if out is None else out
+        out.limbs = cts.limbs
+        vc, vp, vo = cts.view(), pts.view(), out.view()
+        check(self.lib.ckks_multiply_plain_sum(self.h, C.byref(vc), C.byref(vp), C.byref(vo), _stream()))
+        out.scale = scale
+        return out
+
+    def multiply_sum(self, a, b, out=None):
+        """multiply (2x2 -> 3) of every batch entry pair, then add_many, in one kernel"""
+        self._same(a, b)
+        scale = a.scale * b.scale
+        self._scale_ok(scale, a.limbs)
+        out = a[0:1].like(size=3) if out is None else out
+        out.limbs = a.limbs
+        va, vb, vo = a.view(), b.view(), out.view()
+        check(self.lib.ckks_multiply_sum(self.h, C.byref(va), C.byref(vb), C.byref(vo), _stream()))
+        out.scale = scale
+        return out
+
+
+class RotPlan:
+    """a fixed list of rotation steps (one per batch entry) compiled into batched rounds"""
+
+    def __init__(self, ctx, keys, steps):
+        self.ctx, self.keys = ctx, keys
+        self.steps = [int(s) for s in steps]
+        self.batch = len(self.steps)
+        arr = (C.c_int * self.batch)(*self.steps)
+        h = C.c_void_p()
+        check(ctx.lib.ckks_rotplan_create(ctx._h, keys._h, arr, self.batch, C.byref(h)))
+        self._h = h
+        self.keyswitches = int(ctx.lib.ckks_rotplan_keyswitches(h))
+        self.rounds = int(ctx.lib.ckks_rotplan_rounds(h))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.ctx.lib.ckks_rotplan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

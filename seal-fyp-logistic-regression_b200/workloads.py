@@ -1,0 +1,251 @@
+"""The reference's layer-2 HE algorithms, re-expressed over the batched GPU Evaluator.
+
+Every function names the reference function it mirrors (file:line) and issues the SAME evaluator
+op sequence per ciphertext; what changes is only the grouping: independent ciphertexts are
+batched into single kernel launches (rotation plans, fused multiply+add_many), and identical
+sub-computations the reference repeats (the rotations of one ciphertext shared by many linear
+transforms) are computed once.  Both transformations keep every evaluated ciphertext polynomial
+bit-identical to the sequential reference (modular sums are order-independent).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import capi
+from .engine import Ciphertext, RotPlan
+
+
+def force_scale_pow2(ct):
+    """`x.scale() = pow(2, (int)log2(x.scale()))` -- the reference's "manual rescale"
+    (helper.h:489, matrix_multiplication.cpp:119-120, logistic_regression_ckks.cpp:241)"""
+    ct.scale = float(2.0 ** int(math.log2(ct.scale)))
+    return ct
+
+
+class PlanCache:
+    """rotation plans keyed by their step list (plans hold device-side schedules)"""
+
+    def __init__(self, ctx, keys):
+        self.ctx, self.keys, self._plans = ctx, keys, {}
+
+    def get(self, steps):
+        key = tuple(int(s) for s in steps)
+        if key not in self._plans:
+            self._plans[key] = RotPlan(self.ctx, self.keys, key)
+        return self._plans[key]
+
+
+# ------------------------------------------------------------------ linear transforms
+def duplicate_fill(ev, ct, d, keys):
+    """"Fill ct with duplicate": ct + rotate_vector(ct, -d)   (helper.h:241-247)"""
+    return ev.add(ct, ev.rotate_vector(ct, -d, keys))
+
+
+def rotations_of(ev, ct_new, d, plans):
+    """all d rotations rot(ct_new, l), l = 0..d-1, of the hot loop helper.h:252-257, batched"""
+    return ev.rotate_plan(ct_new, plans.get(range(d)))
+
+
+def linear_transform_plain(ev, ct, diags, keys, plans, rots=None):
+    """Linear_Transform_Plain (helper.h:237-262; linear_transformation.cpp:149-174):
+    sum_l diag_l (.) rot(ct + rot(ct,-d), l).  `diags`: Plaintext batch of d diagonals."""
+    d = diags.batch
+    if rots is None:
+        rots = rotations_of(ev, duplicate_fill(ev, ct, d, keys), d, plans)
+    return ev.multiply_plain_sum(rots, diags)
+
+
+def linear_transform_cipher(ev, ct, diag_cts, keys, plans):
+    """Linear_Transform_Cipher (helper.h:212-234): ciphertext diagonals, size-3 result"""
+    d = diag_cts.batch
+    rots = rotations_of(ev, duplicate_fill(ev, ct, d, keys), d, plans)
+    return ev.multiply_sum(rots, diag_cts)
+
+
+def linear_transform_ciphermatrix_plainvector(ev, pt_rotations, ct_diags):
+    """Linear_Transform_CipherMatrix_PlainVector (helper.h:265-278)"""
+    return ev.multiply_plain_sum(ct_diags, pt_rotations)
+
+
+def c_matrix_encode(ev, rows, keys, plans):
+    """C_Matrix_Encode (helper.h:307-322): pack d row ciphertexts into one, row i rotated by -i*d"""
+    d = rows.batch
+    rot = ev.rotate_plan(rows, plans.get([-(i * d) for i in range(d)]))
+    return ev.add_many(rot)
+
+
+def c_matrix_decode(ev, matrix, d, scale, keys, encoder, plans):
+    """C_Matrix_Decode (helper.h:325-360): mask row i with ones, rotate it back by i*d"""
+    masks = np.zeros((d, d * d))
+    for i in range(d):
+        masks[i, i * d:(i + 1) * d] = 1.0
+    mask_pt = encoder.encode(masks, scale, limbs=matrix.limbs)
+    bcast = Ciphertext(matrix.ctx, matrix.data.expand(d, -1, -1, -1).contiguous(), matrix.limbs, matrix.scale)
+    rows = ev.multiply_plain(bcast, mask_pt)
+    return ev.rotate_plan(rows, plans.get([i * d for i in range(d)]))
+
+
+# ------------------------------------------------------------------ permutation matrices (host)
+def u_sigma(d):
+    """get_U_sigma (helper.h:700-742), closed form"""
+    U = np.zeros((d * d, d * d))
+    for i in range(d):
+        for j in range(d):
+            U[d * i + j, d * i + (i + j) % d] = 1.0
+    return U
+
+
+def u_tau(d):
+    """get_U_tau (helper.h:745-785)"""
+    U = np.zeros((d * d, d * d))
+    for i in range(d):
+        for j in range(d):
+            U[d * i + j, d * ((i + j) % d) + j] = 1.0
+    return U
+
+
+def v_k(d, k):
+    """get_V_k (helper.h:788-818)"""
+    U = np.zeros((d * d, d * d))
+    for i in range(d):
+        for j in range(d):
+            U[d * i + j, d * i + (j + k) % d] = 1.0
+    return U
+
+
+def w_k(d, k):
+    """get_W_k (helper.h:821-851)"""
+    U = np.zeros((d * d, d * d))
+    for i in range(d):
+        for j in range(d):
+            U[d * i + j, d * ((i + k) % d) + j] = 1.0
+    return U
+
+
+def u_transpose(d):
+    """get_U_transpose (helper.h:386-413)"""
+    U = np.zeros((d * d, d * d))
+    for i in range(d):
+        for o in range(d):
+            U[d * i + o, d * o + i] = 1.0
+    return U
+
+
+def all_diagonals(U):
+    """get_all_diagonals (helper.h:197-209): diag_l[k] = U[k][(k+l) mod n]"""
+    n = U.shape[0]
+    k = np.arange(n)
+    return np.stack([U[k, (k + l) % n] for l in range(n)])
+
+
+# ------------------------------------------------------------------ matrix multiplication
+def cc_matrix_multiplication(ev, ctA, ctB, d, sigma_diags, tau_diags, V_diags, W_diags, keys, plans):
+    """CC_Matrix_Multiplication (matrix_multiplication.cpp:11-132; matrix_mult_benchmark.cpp:13-71).
+    V_diags / W_diags: lists of d-1 Plaintext batches (d*d diagonals each).
+    The rotations of ctA[0] (resp. ctB[0]) are shared by all V_k (W_k) transforms."""
+    dd = d * d
+    A0 = linear_transform_plain(ev, ctA, sigma_diags, keys, plans)          # Step 1-1
+    B0 = linear_transform_plain(ev, ctB, tau_diags, keys, plans)            # Step 1-2
+    rotA = rotations_of(ev, duplicate_fill(ev, A0, dd, keys), dd, plans)    # Step 2 (shared)
+    rotB = rotations_of(ev, duplicate_fill(ev, B0, dd, keys), dd, plans)
+    A = [ev.multiply_plain_sum(rotA, V_diags[k]) for k in range(d - 1)]
+    B = [ev.multiply_plain_sum(rotB, W_diags[k]) for k in range(d - 1)]
+    # Step 3: rescale the step-2 outputs, multiply, accumulate
+    Ak = _stack(A)
+    Bk = _stack(B)
+    ev.rescale_to_next_inplace(Ak)
+    ev.rescale_to_next_inplace(Bk)
+    ctAB = ev.multiply(A0, B0)
+    ev.mod_switch_to_next_inplace(ctAB)
+    force_scale_pow2(Ak)
+    force_scale_pow2(Bk)
+    rest = ev.multiply_sum(Ak, Bk)
+    if rest.scale != ctAB.scale:
+        raise capi.CkksInvalidArgument("scale mismatch")
+    return ev.add(ctAB, rest)
+
+
+def _stack(cts):
+    """list of batch-1 ciphertexts -> one batch"""
+    data = torch.cat([c.data for c in cts], dim=0)
+    return Ciphertext(cts[0].ctx, data, cts[0].limbs, cts[0].scale)
+
+
+# ------------------------------------------------------------------ dot product
+def cipher_dot_product(ev, ctA, ctB, size, keys):
+    """cipher_dot_product (helper.h:416-502), batched over independent (ctA[b], ctB[b]) pairs:
+    multiply, relinearize, rescale, rotate-and-sum over `size` slots, force the scale."""
+    mult = ev.multiply(ctA, ctB)
+    mult = ev.relinearize(mult, keys)
+    ev.rescale_to_next_inplace(mult)
+    dup = ev.add(mult, ev.rotate_vector(mult, -size, keys))      # "vector has duplicate now"
+    nxt = dup.like()
+    for _ in range(1, size):
+        ev.rotate_vector(dup, 1, keys, out=nxt)                   # rotate_vector_inplace(dup, 1)
+        dup, nxt = nxt, dup
+        ev.add_inplace(mult, dup)
+    return force_scale_pow2(mult)
+
+
+# ------------------------------------------------------------------ polynomial evaluation
+def compute_all_powers(ev, ctx_ct, degree, keys):
+    """compute_all_powers (helper.h:505-547; polynomial.cpp:56-96): x^2..x^degree by the split
+    that minimises multiplicative depth; returns list indexed by power (index 0 unused)"""
+    powers = [None] * (degree + 1)
+    powers[1] = ctx_ct
+    levels = [0] * (degree + 1)
+    for i in range(2, degree + 1):
+        minlevel, cand = i, -1
+        for j in range(1, i // 2 + 1):
+            k = i - j
+            newlevel = max(levels[j], levels[k]) + 1
+            if newlevel < minlevel:
+                cand, minlevel = j, newlevel
+        levels[i] = minlevel
+        if cand < 0:
+            raise RuntimeError("error")
+        temp = ev.mod_switch_to(powers[cand], powers[i - cand].limbs)
+        prod = ev.multiply(temp, powers[i - cand])
+        prod = ev.relinearize(prod, keys)
+        powers[i] = ev.rescale_to_next_inplace(prod)
+    return powers
+
+
+def horner_cipher(ev, x, coeffs, scale, keys, encoder, encryptor):
+    """Horner_cipher (logistic_regression_ckks.cpp:139-205; polynomial.cpp:99-230)"""
+    degree = len(coeffs) - 1
+    temp = encryptor.encrypt(encoder.encode(float(coeffs[degree]), scale))
+    if x.batch > 1:
+        temp = Ciphertext(temp.ctx, temp.data.expand(x.batch, -1, -1, -1).contiguous(), temp.limbs, temp.scale)
+    x = ev.mod_switch_to(x, x.limbs)
+    for i in range(degree - 1, -1, -1):
+        if x.limbs > temp.limbs:
+            ev.mod_switch_to_inplace(x, temp.limbs)
+        elif x.limbs < temp.limbs:
+            ev.mod_switch_to_inplace(temp, x.limbs)
+        temp = ev.multiply(temp, x)
+        temp = ev.relinearize(temp, keys)
+        ev.rescale_to_next_inplace(temp)
+        temp.scale = float(2.0 ** 40)                                  # "Manual rescale" (:195)
+        ev.add_plain_inplace(temp, encoder.encode(float(coeffs[i]), scale, limbs=temp.limbs))
+    return temp
+
+
+def tree_cipher(ev, x, coeffs, scale, keys, encoder, encryptor):
+    """Tree_cipher (logistic_regression_ckks.cpp:55-137; polynomial.cpp:233-359)"""
+    degree = len(coeffs) - 1
+    powers = compute_all_powers(ev, x, degree, keys)
+    enc_result = encryptor.encrypt(encoder.encode(float(coeffs[0]), scale))
+    if x.batch > 1:
+        enc_result = Ciphertext(enc_result.ctx, enc_result.data.expand(x.batch, -1, -1, -1).contiguous(),
+                                enc_result.limbs, enc_result.scale)
+    for i in range(1, degree + 1):
+        pt = encoder.encode(float(coeffs[i]), scale, limbs=powers[i].limbs)
+        temp = ev.multiply_plain(powers[i], pt)
+        ev.rescale_to_next_inplace(temp)
+        ev.mod_switch_to_inplace(enc_result, temp.limbs)
+        force_scale_pow2(enc_result)
+        temp.scale = float(2.0 ** int(math.log2(enc_result.scale)))
+        ev.add_inplace(enc_result, temp)
+    return enc_result
