@@ -91,7 +91,7 @@ class CKKSEncoder:
     def decode(self, pt):
         """Plaintext (batch B) -> float64 [B][slots]"""
         n, L = self.ctx.n, pt.limbs
-        t = pt.data[:, 0, :L, :].contiguous()
+        t = pt.data[:, 0, :L, :].clone()          # the inverse NTT runs in place: keep the plaintext intact
         self.ev.ntt_inverse(t)
         res = t.cpu().numpy().view(np.uint64)
         primes = self.ctx.primes[:L]
