@@ -1,0 +1,482 @@
+#!/usr/bin/env python
+"""bench.py -- encrypted logistic-regression training throughput on B200 (BASELINE.json metric
+"CKKS LR train epochs/s; rotate/relin keyswitch ops/s at N=2^14,2^15").
+
+Workload (BASELINE.json configs[4]): synthetic 8 features x 32768 samples
+per GPU, N = 32768, coeff_modulus {60, 40 x 8, 60}, scale 2^40, tree-method degree-7 sigmoid,
+column layout with mini-batches of 8192 samples (4 per GPU).  One step = one epoch over the
+GPU's shard: for every mini-batch  z = sum_j multiply(col_j, w_j); relinearize; rescale;
+Tree_cipher(z); sub labels; per feature cipher_dot_product(col_j, pred - y, 8192) (1 relinearize
++ 8192 Galois key switches at L = 3) and the one-hot mask; add_many; rescale -- then the partial
+gradient ciphertexts of all GPUs are all-gathered (NCCL) and combined with the mod-q add kernel,
+and the weight update (multiply_plain lr/R, rescale, sub, negate) is applied.  Weak scaling: every
+GPU holds its own 8 x 32768 shard.
+
+  python bench.py --gpus N --steps K --warmup W      (N > 1 under torch.distributed.run)
+  python bench.py --impl reference ...               CPU arm: the SEAL-3.4.5-equivalent oracle
+                                                     (SEAL itself is not installable here) on the
+                                                     host cores, bounded sample, same metric
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "seal-fyp-logistic-regression_b200"
+
+LOG_N = 15
+BITS = [60] + [40] * 8 + [60]
+SCALE = 2.0 ** 40
+C_FEAT = 8
+R_PER_GPU = 32768
+B_MINI = 8192
+DEGREE = 7
+LR = 0.1
+METRIC = "ckks_lr_train_epochs_per_s"
+UNIT = "epochs/s"
+
+
+def ks_bytes(L, n, relin=False):
+    """algorithmic bytes of one key switch: rotate (2L^2+6L)*8N, relin (2L^2+7L)*8N"""
+    return (2 * L * L + (7 if relin else 6) * L) * 8 * n
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.samples:
+            if ts < t0 or ts > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ data
+def synthetic_shard(seed):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(0.0, 1.0, (R_PER_GPU, C_FEAT))
+    w_true = rng.uniform(-1, 1, C_FEAT)
+    y = (1.0 / (1.0 + np.exp(-X @ w_true)) > rng.uniform(0, 1, R_PER_GPU)).astype(np.float64)
+    return X, y
+
+
+def epoch_op_counts():
+    """evaluator ops of one epoch on one GPU, by (op, limbs): used to scale the CPU sample"""
+    M, C, B = R_PER_GPU // B_MINI, C_FEAT, B_MINI
+    top = len(BITS) - 1
+    ops = []
+    ops += [("multiply", top, M * C), ("add3", top, M * (C - 1)), ("relinearize", top, M), ("rescale", top, M)]
+    # tree degree 7: x at L8; x^2 L8->7, x^3 / x^4 at L7->6, x^5..x^7 at L6->5
+    for lvl, cnt in ((top - 1, 1), (top - 2, 2), (top - 3, 3)):
+        ops += [("multiply", lvl, M * cnt), ("relinearize", lvl, M * cnt), ("rescale", lvl, M * cnt)]
+    ops += [("multiply_plain", top - 3, M * 7), ("rescale", top - 3, M * 7), ("add", top - 5, M * 8)]
+    Lp = top - 5                                   # level of the prediction (4)
+    ops += [("multiply", Lp, M * C), ("relinearize", Lp, M * C), ("rescale", Lp, M * C)]
+    ops += [("rotate", Lp - 1, M * C * B), ("add", Lp - 1, M * C * B)]
+    ops += [("multiply_plain", Lp - 1, M * C), ("add", Lp - 1, M * C), ("rescale", Lp - 1, 1)]
+    return ops
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_reference(budget_s=15.0, threads=None):
+    """Time the CPU oracle (SEAL-3.4.5-equivalent restatement) on a bounded sample of the epoch:
+    the op that carries >99.9% of the work -- one Galois key switch + add at L = 3, N = 32768 -- is
+    run on `threads` independent ciphertexts in parallel for ~budget seconds; the remaining op types
+    are timed once each; the epoch time is sum(count x time)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po
+    threads = threads or (os.cpu_count() or 1)
+    primes = po.coeff_modulus_create(LOG_N, BITS)
+    orc = po.Oracle(LOG_N, primes)
+    sk = orc.gen_secret(1)
+    rlk = orc.gen_relin_key(2, sk)
+    g = orc.galois_elt(1)
+    gk = orc.gen_galois_key(3, sk, g)
+    rng = np.random.default_rng(0)
+    n = 1 << LOG_N
+
+    def rand_ct(S, L):
+        return np.stack([rng.integers(0, p, size=(S, n), dtype=np.uint64) for p in primes[:L]], axis=1)
+
+    L3 = len(BITS) - 1 - 6
+    cts = [rand_ct(2, L3) for _ in range(threads)]
+    t0 = time.perf_counter()
+    orc.add(orc.apply_galois(cts[0], g, gk), cts[0])
+    t_one = time.perf_counter() - t0
+    iters = max(2, int(budget_s / max(t_one, 1e-4)))
+
+    def chain(ct):
+        acc, dup = ct, ct
+        for _ in range(iters):
+            dup = orc.apply_galois(dup, g, gk)
+            acc = orc.add(acc, dup)
+        return acc
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(chain, cts))
+    wall = time.perf_counter() - t0
+    t_rot = wall / (iters * threads)              # effective seconds per (rotate + add) with all threads busy
+
+    def once(fn):
+        t = time.perf_counter()
+        fn()
+        return (time.perf_counter() - t) / threads   # the other ops parallelise over ciphertexts the same way
+
+    cache = {}
+
+    def op_time(op, L):
+        key = (op, L)
+        if key in cache:
+            return cache[key]
+        a2, b2, a3, pt = rand_ct(2, L), rand_ct(2, L), rand_ct(3, L), rand_ct(1, L)[0]
+        fns = {
+            "multiply": lambda: orc.multiply(a2, b2),
+            "add3": lambda: orc.add(a3, a3),
+            "add": lambda: orc.add(a2, b2),
+            "relinearize": lambda: orc.relinearize(a3, rlk),
+            "rescale": lambda: orc.rescale(a2),
+            "multiply_plain": lambda: orc.multiply_plain(a2, pt),
+        }
+        cache[key] = once(fns[op])
+        return cache[key]
+
+    total = 0.0
+    for op, L, cnt in epoch_op_counts():
+        if op == "rotate":
+            total += cnt * t_rot
+        elif op == "add" and L == L3 and cnt > 1000:
+            continue                                # included in t_rot
+        else:
+            total += cnt * op_time(op, L)
+    return {
+        "value": 1.0 / total, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": "%d x %d (Galois key switch + add) at N=32768, L=%d on %d threads in %.1f s (%.2f ms per op per thread); "
+                  "other op types timed once; epoch time = sum(count x time) = %.0f s" % (
+                      threads, iters, L3, threads, wall, 1e3 * t_rot * threads, total),
+        "rotate_add_ms_per_thread": 1e3 * t_rot * threads,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    budget = min(20.0, 60.0 / (steps + args.warmup + 1))
+    vals = []
+    for i in range(args.warmup + steps):
+        r = cpu_reference(budget_s=budget)
+        if i >= args.warmup:
+            vals.append(r)
+    value = float(np.mean([v["value"] for v in vals]))
+    cb = dict(vals[-1])
+    cb["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "SEAL is not installable here (no source in the reference, no network); this arm times the "
+                "SEAL-3.4.5-equivalent CPU oracle on a bounded sample of the same workload, all host threads",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "encrypted LR training epoch, synthetic %d features x %d samples per GPU, N=32768, "
+                    "coeff_modulus {60,40x8,60}, scale 2^40, tree degree-%d sigmoid, column layout, "
+                    "mini-batches of %d" % (C_FEAT, R_PER_GPU, DEGREE, B_MINI),
+        "poly_modulus_degree": 1 << LOG_N, "coeff_modulus_bits": BITS, "features": C_FEAT,
+        "samples_per_gpu": R_PER_GPU, "mini_batch": B_MINI, "sigmoid": "tree degree %d" % DEGREE,
+        "parallelism": "mini-batch shards x%d, all-gather + mod-q add of gradient ciphertexts" % n_gpus,
+        "l2_policy": "inputs exceed L2 (151 MB of column ciphertexts + 2 x 47 MB keys + 255 MB workspace per step)",
+    }
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CKKS engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module(PKG)
+    pkg.build()
+    eng = pkg.load_engine()
+    client = importlib.import_module(PKG + ".client")
+    lr = importlib.import_module(PKG + ".lr")
+    wl = importlib.import_module(PKG + ".workloads")
+
+    primes = _primes()
+    ctx = eng.Context(LOG_N, primes, device=local)
+    ev = eng.Evaluator(ctx)
+    enc = client.CKKSEncoder(ctx)
+    kg = client.KeyGenerator(ctx, seed=1234)          # same keys on every rank (one client)
+    keys = kg.keyset(steps=[1, -B_MINI])
+    encr = client.Encryptor(ctx, kg.public_key(), seed=100 + rank)
+    decr = client.Decryptor(ctx, kg.secret_key())
+    slots = ctx.n // 2
+    M = R_PER_GPU // B_MINI
+
+    X, y = synthetic_shard(seed=10 + rank)
+    lay = lr.ColumnLayout(R_PER_GPU, C_FEAT, B_MINI, slots)
+    w0 = np.random.default_rng(5).uniform(-1, 1, C_FEAT)
+    wvec = np.zeros(slots)
+    wvec[:C_FEAT] = w0
+    # client side (untimed): encode + encrypt, kept in PINNED host memory for the e2e leg
+    cols_d = encr.encrypt(enc.encode(lay.columns(X), SCALE))
+    labs_d = encr.encrypt(enc.encode(lay.labels(y), SCALE))
+    wb_d = encr.encrypt(enc.encode(np.repeat(w0[:, None], slots, axis=1), SCALE))
+    wct_d = encr.encrypt(enc.encode(wvec, SCALE))
+    host = {k: v.data.cpu().pin_memory() for k, v in (("cols", cols_d), ("labs", labs_d), ("wb", wb_d), ("w", wct_d))}
+    h2d_bytes = sum(t.numel() * 8 for t in host.values())
+    R_total = R_PER_GPU * world
+
+    ctx.reserve(M * C_FEAT, ctx.top_limbs)
+
+    def epoch(cols, labs, wb, wct):
+        grad = lr.column_epoch_gradient(ev, cols, labs, wb, C_FEAT, B_MINI, SCALE, keys, enc, encr,
+                                        degree=DEGREE, method="tree")
+        if world > 1:
+            gathered = torch.empty((world,) + tuple(grad.data.shape[1:]), dtype=grad.data.dtype, device=grad.data.device)
+            dist.all_gather_into_tensor(gathered, grad.data)
+            grad = ev.add_many(eng.Ciphertext(ctx, gathered, grad.limbs, grad.scale))   # mod-q add of the partials
+        return grad, lr.apply_gradient(ev, grad, wct, LR, R_total, SCALE, enc)
+
+    def epoch_resident():
+        return epoch(cols_d, labs_d, wb_d, wct_d)
+
+    out_host = torch.empty((1, 2, ctx.top_limbs, ctx.n), dtype=torch.int64).pin_memory()
+
+    def epoch_e2e():
+        dev = {k: t.to(ctx.device, non_blocking=True) for k, t in host.items()}
+        top = ctx.top_limbs
+        grad, neww = epoch(eng.Ciphertext(ctx, dev["cols"], top, SCALE), eng.Ciphertext(ctx, dev["labs"], top, SCALE),
+                           eng.Ciphertext(ctx, dev["wb"], top, SCALE), eng.Ciphertext(ctx, dev["w"], top, SCALE))
+        out_host[:, :, : neww.limbs].copy_(neww.data[:, :, : neww.limbs], non_blocking=True)
+        return grad, neww
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, warmup, steps):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ctx.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=ctx.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, ctx.launch_count(), t0, t1
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, (grad, neww), launches, t0, t1 = timed(epoch_resident, args.warmup, args.steps)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    value = world * args.steps / (ms / 1e3)
+
+    # correctness gate on the timed computation: decrypted weights vs plaintext LR on this shard
+    got = enc.decode(decr.decrypt(neww))[0, :C_FEAT]
+    if world == 1:
+        want = lr.plain_epoch(X, y, w0, LR, DEGREE)
+        err = float(np.abs(got - want).max())
+        assert err < 1e-3, "decrypted weights differ from plaintext LR by %g" % err
+    else:
+        err = None
+
+    ms_e2e, _, _, _, _ = timed(epoch_e2e, 1, max(1, min(args.steps, 2)))
+    e2e_steps = max(1, min(args.steps, 2))
+    value_e2e = world * e2e_steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel family: the batched Galois key switch of the dot-product
+    # chain (M*C ciphertexts, L = 3) -- 8 launches per key switch, timed live with CUDA events
+    Lk = ctx.top_limbs - 6
+    nb = M * C_FEAT
+    a = ctx.empty(nb, 2, Lk, cap=ctx.top_limbs, scale=SCALE)
+    a.data.random_(0, 1 << 39)
+    b = a.like()
+    g1 = ctx.galois_elt(1)
+    for _ in range(5):
+        ev.apply_galois(a, g1, keys, out=b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 200
+    e0.record()
+    for _ in range(reps // 2):
+        ev.apply_galois(a, g1, keys, out=b)
+        ev.apply_galois(b, g1, keys, out=a)
+    e1.record()
+    torch.cuda.synchronize()
+    ks_ms = e0.elapsed_time(e1) / reps
+    alg = nb * ks_bytes(Lk, ctx.n)
+    peak, peak_src = peaks()
+    achieved = alg / (ks_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "kernel": "Galois key switch pipeline (k_ks_intt_row, k_inv_col, k_ks_modup_col, k_ks_mac, k_inv_row, "
+                  "k_inv_col, k_md_fwd_col, k_md_fwd_row), batch %d, N=32768, L=%d" % (nb, Lk),
+        "algorithmic_bytes_per_launch_group": alg, "ms_per_launch_group": ks_ms, "peak_source": peak_src,
+        "keyswitch_per_s": nb / (ks_ms * 1e-3),
+    }
+    ks_extra = keyswitch_sweep(torch, eng, ctx, ev, keys) if rank == 0 and not args.no_sweep else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference(budget_s=args.cpu_budget)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": int(out_host[:, :, : neww.limbs].numel() * 8), "steps": e2e_steps},
+            "gpu_launches": int(launches) * world,
+            "gpu_launches_per_step_per_gpu": int(launches) // args.steps,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "keyswitch_ops_per_s": ks_extra,
+            "check": {"max_abs_err_vs_plaintext_lr": err, "tolerance": 1e-3},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _primes():
+    """CoeffModulus::Create(32768, {60, 40 x 8, 60}) -- product-side restatement of SEAL's prime
+    search (first occurrence of a size gets the smallest of that size's primes)."""
+    pkg = importlib.import_module(PKG + ".params")
+    return pkg.coeff_modulus_create(LOG_N, BITS)
+
+
+def keyswitch_sweep(torch, eng, ctx15, ev15, keys15):
+    """second half of the metric: rotate / relinearize key-switch ops/s at N = 2^14 and 2^15"""
+    client = importlib.import_module(PKG + ".client")
+    params = importlib.import_module(PKG + ".params")
+    out = {}
+    peak, _ = peaks()
+    for log_n, bits, batch in ((14, [60, 40, 40, 60], 256), (14, [60] + [40] * 7 + [60], 64), (15, BITS, 32)):
+        if log_n == 15:
+            ctx, ev, keys = ctx15, ev15, keys15
+        else:
+            ctx = eng.Context(log_n, params.coeff_modulus_create(log_n, bits))
+            ev = eng.Evaluator(ctx)
+            keys = client.KeyGenerator(ctx, seed=3).keyset(steps=[1])
+        L = ctx.top_limbs
+        a = ctx.empty(batch, 2, L, scale=SCALE)
+        a.data.random_(0, 1 << 39)
+        a3 = ctx.empty(batch, 3, L, scale=SCALE)
+        a3.data.random_(0, 1 << 39)
+        b, b2 = a.like(), a.like()
+        g1 = ctx.galois_elt(1)
+        res = {}
+        for name, fn, relin in (("rotate", lambda: ev.apply_galois(a, g1, keys, out=b), False),
+                                ("relinearize", lambda: ev.relinearize(a3, keys, out=b2), True)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            gbs = batch * ks_bytes(L, ctx.n, relin) / (ms * 1e-3) / 1e9
+            res[name] = {"ops_per_s": batch / (ms * 1e-3), "batch": batch, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+        out["N=%d,L=%d" % (ctx.n, L)] = res
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the key-switch ops/s sweep")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
