@@ -267,7 +267,7 @@ def run_gpu(args):
     eng = pkg.load_engine()
     client = importlib.import_module(PKG + ".client")
     lr = importlib.import_module(PKG + ".lr")
-    wl = importlib.import_module(PKG + ".workloads")
+    par = importlib.import_module(PKG + ".parallel")
 
     primes = _primes()
     ctx = eng.Context(LOG_N, primes, device=local)
@@ -299,10 +299,7 @@ def run_gpu(args):
     def epoch(cols, labs, wb, wct):
         grad = lr.column_epoch_gradient(ev, cols, labs, wb, C_FEAT, B_MINI, SCALE, keys, enc, encr,
                                         degree=DEGREE, method="tree")
-        if world > 1:
-            gathered = torch.empty((world,) + tuple(grad.data.shape[1:]), dtype=grad.data.dtype, device=grad.data.device)
-            dist.all_gather_into_tensor(gathered, grad.data)
-            grad = ev.add_many(eng.Ciphertext(ctx, gathered, grad.limbs, grad.scale))   # mod-q add of the partials
+        grad = par.combine_partials(ev, grad)     # all-gather of the partial ciphertexts + mod-q add kernel
         return grad, lr.apply_gradient(ev, grad, wct, LR, R_total, SCALE, enc)
 
     def epoch_resident():

@@ -1,0 +1,75 @@
+"""CPU, world_size 2 over gloo: the multi-GPU protocol (shard -> partial -> all-gather -> mod-q
+add) reproduces the single-process result bit for bit.  The mod-q add runs on the oracle here
+(the CUDA kernel needs a GPU; the GPU suite covers it through ckks_add_many)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = "seal-fyp-logistic-regression_b200"
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pyoracle as po
+        par = importlib.import_module(PKG + ".parallel")
+        log_n = 12
+        primes = po.coeff_modulus_create(log_n, [50, 40, 50])
+        orc = po.Oracle(log_n, primes)
+        rng = np.random.default_rng(7)          # same stream on every rank
+        d, L = 9, 2
+        cts = np.stack([np.stack([rng.integers(0, p, size=(2, orc.n), dtype=np.uint64) for p in primes[:L]], axis=1)
+                        for _ in range(d)])
+        mine = par.shard_units(d, rank, world)
+        assert mine == list(range(rank, d, world))
+        part = cts[mine[0]]
+        for u in mine[1:]:
+            part = orc.add(part, cts[u])
+        g = par.gather_partials(torch.from_numpy(part.view(np.int64).copy()))
+        assert g.shape[0] == world
+        g = g.numpy().view(np.uint64)
+        total = g[0]
+        for r in range(1, world):
+            total = orc.add(total, g[r])
+        want = cts[0]
+        for u in range(1, d):
+            want = orc.add(want, cts[u])
+        ok = bool(np.array_equal(total, want))
+        # a non-modular integer sum (what ncclSum would do) must differ somewhere
+        naive = (g[0] + g[1])
+        ok_naive_differs = bool(not np.array_equal(naive, want))
+        ret[rank] = (ok, ok_naive_differs, len(mine))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_sum_matches_sequential_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        ok, naive_differs, n = ret[r]
+        assert ok and naive_differs
+    assert sum(ret[r][2] for r in range(world)) == 9
+
+
+def test_shard_units_partition():
+    par = importlib.import_module(PKG + ".parallel")
+    for n in (1, 7, 64, 128):
+        for G in (1, 2, 4, 8):
+            parts = [par.shard_units(n, r, G) for r in range(G)]
+            assert sorted(sum(parts, [])) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
