@@ -82,6 +82,7 @@ int ckks_host_alloc(size_t bytes, void **out);   /* pinned */
 int ckks_host_free(void *p);
 int ckks_upload(ckks_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, ckks_stream s);
 int ckks_download(ckks_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, ckks_stream s);
+int ckks_copy(ckks_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes, ckks_stream s);   /* device to device */
 int ckks_stream_sync(ckks_ctx *ctx, ckks_stream s);
 
 /* ---- negacyclic NTT (SEAL util::ntt_negacyclic_harvey / inverse_...): n_polys x limbs limbs in

@@ -209,6 +209,10 @@ extern "C" int ckks_download(ckks_ctx *, void *dst, const void *src, size_t byte
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
     return CKKS_OK;
 }
+extern "C" int ckks_copy(ckks_ctx *, void *dst, const void *src, size_t bytes, ckks_stream s) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+    return CKKS_OK;
+}
 extern "C" int ckks_stream_sync(ckks_ctx *, ckks_stream s) {
     CU(cudaStreamSynchronize((cudaStream_t)s));
     return CKKS_OK;

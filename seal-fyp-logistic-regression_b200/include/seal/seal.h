@@ -1,0 +1,1100 @@
+// seal/seal.h -- source-compatible shim of the Microsoft SEAL surface that
+// MarwanNour/SEAL-FYP-Logistic-Regression uses on its CKKS hot path, backed by the B200 engine
+// (libckks_b200.so, include/ckks_b200.h).  The reference reaches SEAL through
+// `#include "seal/seal.h"` + `using namespace seal;` (helper.h:4-7); put this directory on the
+// include path and link libckks_b200.so instead of SEAL::seal.
+//
+// It accepts the UNION of the two API spellings found in the reference:
+//   3.4/3.5: scheme_type::CKKS, SEALContext::Create(parms) -> shared_ptr, keygen.public_key(),
+//            keygen.relin_keys(), keygen.galois_keys()
+//   3.6    : scheme_type::ckks, SEALContext context(parms), keygen.create_public_key(pk), ...
+//
+// Ownership / semantics follow SEAL: value types, inputs by const&, destination overwritten,
+// std::invalid_argument / std::logic_error on misuse.  Ciphertext / Plaintext / key data live in
+// device memory (copy-on-write, so the reference's by-value parameter passing stays cheap); every
+// Evaluator member enqueues kernels on one CUDA stream and returns; decrypt / decode synchronise.
+// Ring arithmetic is always done by the GPU engine: there is no CPU fallback in this shim.  The
+// host only samples randomness and does the floating-point canonical embedding.
+//
+// Not provided (outside the reference's CKKS path): BFV evaluation, IntegerEncoder, BatchEncoder,
+// serialization, ciphertext sizes above 3.
+#pragma once
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ckks_b200.h"
+
+namespace seal {
+
+using parms_id_type = std::array<std::uint64_t, 4>;
+static const parms_id_type parms_id_zero = {0, 0, 0, 0};
+
+enum class scheme_type : std::uint8_t { none = 0, BFV = 1, bfv = 1, CKKS = 2, ckks = 2 };
+enum class sec_level_type : int { none = 0, tc128 = 128, tc192 = 192, tc256 = 256 };
+
+class MemoryPoolHandle {};
+struct MemoryManager {
+    static MemoryPoolHandle GetPool() { return MemoryPoolHandle(); }
+};
+
+namespace detail {
+
+inline void check(int rc) {
+    if (rc == CKKS_OK) return;
+    std::string msg = ckks_last_error();
+    if (rc == CKKS_ERR_INVALID) throw std::invalid_argument(msg);
+    if (rc == CKKS_ERR_LOGIC) throw std::logic_error(msg);
+    if (rc == CKKS_ERR_NOMEM) throw std::bad_alloc();
+    throw std::runtime_error(msg);
+}
+
+typedef unsigned __int128 u128;
+inline std::uint64_t mulmod(std::uint64_t a, std::uint64_t b, std::uint64_t p) { return (std::uint64_t)((u128)a * b % p); }
+inline std::uint64_t powmod(std::uint64_t a, std::uint64_t e, std::uint64_t p) {
+    std::uint64_t r = 1;
+    a %= p;
+    for (; e; e >>= 1, a = mulmod(a, a, p))
+        if (e & 1) r = mulmod(r, a, p);
+    return r;
+}
+inline bool is_prime(std::uint64_t n) {
+    if (n < 2) return false;
+    for (std::uint64_t w : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+        if (n % w == 0) return n == w;
+    }
+    std::uint64_t d = n - 1;
+    int r = 0;
+    while (!(d & 1)) d >>= 1, ++r;
+    for (std::uint64_t w : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+        std::uint64_t x = powmod(w, d, n);
+        if (x == 1 || x == n - 1) continue;
+        bool comp = true;
+        for (int i = 1; i < r && comp; ++i) {
+            x = mulmod(x, x, n);
+            if (x == n - 1) comp = false;
+        }
+        if (comp) return false;
+    }
+    return true;
+}
+inline int bit_length(std::uint64_t v) {
+    int b = 0;
+    while (v) ++b, v >>= 1;
+    return b;
+}
+inline std::uint32_t bitrev(std::uint32_t v, int bits) {
+    std::uint32_t r = 0;
+    for (int i = 0; i < bits; ++i, v >>= 1) r = (r << 1) | (v & 1);
+    return r;
+}
+
+}  // namespace detail
+
+// ------------------------------------------------------------------------------------ moduli
+class SmallModulus {
+public:
+    SmallModulus(std::uint64_t v = 0) : value_(v) {}
+    std::uint64_t value() const { return value_; }
+    int bit_count() const { return detail::bit_length(value_); }
+    bool is_zero() const { return value_ == 0; }
+    bool operator==(const SmallModulus &o) const { return value_ == o.value_; }
+
+private:
+    std::uint64_t value_;
+};
+using Modulus = SmallModulus;
+
+class CoeffModulus {
+public:
+    // SEAL CoeffModulus::MaxBitCount (128-bit classical security)
+    static int MaxBitCount(std::size_t n, sec_level_type = sec_level_type::tc128) {
+        switch (n) {
+        case 1024: return 27;
+        case 2048: return 54;
+        case 4096: return 109;
+        case 8192: return 218;
+        case 16384: return 438;
+        case 32768: return 881;
+        default: return 0;
+        }
+    }
+    // SEAL CoeffModulus::Create: per bit size the c largest primes = 1 mod 2N below 2^bits; the
+    // request is served in order from the smallest of each size
+    static std::vector<SmallModulus> Create(std::size_t n, std::vector<int> bits) {
+        std::map<int, std::vector<std::uint64_t>> pool;
+        for (int b : bits) {
+            if (b < 2 || b > 60) throw std::invalid_argument("bit_sizes is invalid");
+            pool[b];
+        }
+        for (auto &kv : pool) {
+            std::size_t need = (std::size_t)std::count(bits.begin(), bits.end(), kv.first);
+            std::uint64_t step = 2 * (std::uint64_t)n, v = (1ull << kv.first) - step + 1;
+            while (kv.second.size() < need && v > (1ull << (kv.first - 1))) {
+                if (detail::is_prime(v)) kv.second.push_back(v);
+                v -= step;
+            }
+            if (kv.second.size() < need) throw std::logic_error("failed to find enough qualifying primes");
+        }
+        std::vector<SmallModulus> out;
+        for (int b : bits) {
+            out.emplace_back(pool[b].back());
+            pool[b].pop_back();
+        }
+        return out;
+    }
+    // SEAL default_coeff_modulus_128
+    static std::vector<SmallModulus> BFVDefault(std::size_t n, sec_level_type = sec_level_type::tc128) {
+        static const std::map<std::size_t, std::vector<std::uint64_t>> t = {
+            {4096, {0xffffee001, 0xffffc4001, 0x1ffffe0001}},
+            {8192, {0x7fffffd8001, 0x7fffffc8001, 0xfffffffc001, 0xffffff6c001, 0xfffffebc001}},
+            {16384, {0xfffffffd8001, 0xfffffffa0001, 0xfffffff00001, 0x1fffffff68001, 0x1fffffff50001, 0x1ffffffee8001,
+                     0x1ffffffea0001, 0x1ffffffe88001, 0x1ffffffe48001}},
+            {32768, {0x7fffffffe90001, 0x7fffffffbf0001, 0x7fffffffbd0001, 0x7fffffffba0001, 0x7fffffffaa0001,
+                     0x7fffffffa50001, 0x7fffffff9f0001, 0x7fffffff7e0001, 0x7fffffff770001, 0x7fffffff380001,
+                     0x7fffffff330001, 0x7fffffff2d0001, 0x7fffffff170001, 0x7fffffff150001, 0x7ffffffef00001,
+                     0xfffffffff70001}}};
+        auto it = t.find(n);
+        if (it == t.end()) throw std::invalid_argument("poly_modulus_degree is invalid");
+        return std::vector<SmallModulus>(it->second.begin(), it->second.end());
+    }
+};
+
+class EncryptionParameters {
+public:
+    EncryptionParameters(scheme_type s = scheme_type::none) : scheme_(s) {}
+    void set_poly_modulus_degree(std::size_t n) { n_ = n; }
+    void set_coeff_modulus(const std::vector<SmallModulus> &m) { coeff_ = m; }
+    void set_plain_modulus(const SmallModulus &m) { plain_ = m; }
+    void set_plain_modulus(std::uint64_t m) { plain_ = SmallModulus(m); }
+    scheme_type scheme() const { return scheme_; }
+    std::size_t poly_modulus_degree() const { return n_; }
+    const std::vector<SmallModulus> &coeff_modulus() const { return coeff_; }
+    const SmallModulus &plain_modulus() const { return plain_; }
+
+private:
+    scheme_type scheme_;
+    std::size_t n_ = 0;
+    std::vector<SmallModulus> coeff_;
+    SmallModulus plain_;
+};
+
+// ------------------------------------------------------------------------------------ engine glue
+namespace detail {
+
+// one GPU engine context per distinct parameter set, shared by every SEALContext built from it
+// (the reference rebuilds SEALContext inside helpers on every call, helper.h:239-240)
+struct Engine {
+    ckks_ctx *ctx = nullptr;
+    int log_n = 0, K = 0;
+    std::size_t n = 0;
+    std::vector<std::uint64_t> primes;
+    std::map<std::size_t, std::vector<std::uint64_t *>> pool;   // free device buffers by word count
+    std::mutex mu;
+    ~Engine() {
+        for (auto &kv : pool)
+            for (auto p : kv.second) ckks_dev_free(ctx, p);
+        if (ctx) ckks_ctx_destroy(ctx);
+    }
+    std::uint64_t *alloc(std::size_t words) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto &v = pool[words];
+            if (!v.empty()) {
+                auto p = v.back();
+                v.pop_back();
+                return p;
+            }
+        }
+        void *p = nullptr;
+        check(ckks_dev_alloc(ctx, words * 8, &p));
+        return (std::uint64_t *)p;
+    }
+    void release(std::uint64_t *p, std::size_t words) {
+        std::lock_guard<std::mutex> g(mu);
+        pool[words].push_back(p);   // all work is ordered on one stream, so reuse is safe
+    }
+    static std::shared_ptr<Engine> get(std::size_t n, const std::vector<std::uint64_t> &primes) {
+        static std::mutex m;
+        static std::map<std::pair<std::size_t, std::vector<std::uint64_t>>, std::weak_ptr<Engine>> reg;
+        std::lock_guard<std::mutex> g(m);
+        auto key = std::make_pair(n, primes);
+        if (auto sp = reg[key].lock()) return sp;
+        auto e = std::make_shared<Engine>();
+        e->n = n;
+        e->log_n = bit_length(n) - 1;
+        e->K = (int)primes.size();
+        e->primes = primes;
+        check(ckks_ctx_create(e->log_n, e->K, primes.data(), 0, &e->ctx));
+        reg[key] = e;
+        return e;
+    }
+};
+
+struct DevBuf {
+    std::shared_ptr<Engine> eng;
+    std::uint64_t *p = nullptr;
+    std::size_t words = 0;
+    DevBuf(std::shared_ptr<Engine> e, std::size_t w) : eng(std::move(e)), p(eng->alloc(w)), words(w) {}
+    ~DevBuf() { eng->release(p, words); }
+    DevBuf(const DevBuf &) = delete;
+};
+using BufPtr = std::shared_ptr<DevBuf>;
+
+inline parms_id_type make_id(const Engine &e, int limbs) {
+    std::uint64_t h = 1469598103934665603ull;
+    for (int j = 0; j < limbs; j++) h = (h ^ e.primes[j]) * 1099511628211ull;
+    return {(std::uint64_t)limbs, (std::uint64_t)e.n, h, 0x434b4b53ull};
+}
+
+// polynomial container shared by Plaintext and Ciphertext: [size][cap][N] device words
+struct Poly {
+    std::shared_ptr<Engine> eng;
+    BufPtr buf;
+    int size = 0, limbs = 0, cap = 0;
+    double scale = 1.0;
+    void allocate(std::shared_ptr<Engine> e, int size_, int limbs_) {
+        eng = std::move(e);
+        size = size_;
+        limbs = cap = limbs_;
+        buf = std::make_shared<DevBuf>(eng, (std::size_t)size * cap * eng->n);
+    }
+    ckks_view view() const {
+        ckks_view v;
+        v.data = buf->p;
+        v.batch_stride = (std::uint64_t)size * cap * eng->n;
+        v.poly_stride = (std::uint64_t)cap * eng->n;
+        v.batch = 1;
+        v.size = size;
+        v.limbs = limbs;
+        v.reserved = 0;
+        return v;
+    }
+    void make_unique() {   // copy-on-write before an in-place update
+        if (buf && buf.use_count() > 1) {
+            auto nb = std::make_shared<DevBuf>(eng, buf->words);
+            check(ckks_copy(eng->ctx, nb->p, buf->p, buf->words * 8, nullptr));
+            buf = nb;
+        }
+    }
+    parms_id_type parms_id() const { return eng ? make_id(*eng, limbs) : parms_id_zero; }
+};
+
+}  // namespace detail
+
+// ------------------------------------------------------------------------------------ context
+class SEALContext {
+public:
+    class ContextData {
+    public:
+        const EncryptionParameters &parms() const { return parms_; }
+        const parms_id_type &parms_id() const { return id_; }
+        std::size_t chain_index() const { return chain_index_; }
+        int total_coeff_modulus_bit_count() const { return total_bits_; }
+        std::shared_ptr<const ContextData> next_context_data() const { return next_; }
+        std::shared_ptr<const ContextData> prev_context_data() const { return prev_.lock(); }
+
+    private:
+        friend class SEALContext;
+        EncryptionParameters parms_;
+        parms_id_type id_;
+        std::size_t chain_index_ = 0;
+        int total_bits_ = 0;
+        std::shared_ptr<const ContextData> next_;
+        std::weak_ptr<const ContextData> prev_;
+    };
+
+    explicit SEALContext(const EncryptionParameters &parms, bool = true, sec_level_type = sec_level_type::tc128) {
+        if (parms.scheme() != scheme_type::CKKS)
+            throw std::invalid_argument("this engine implements the CKKS path only");
+        std::vector<std::uint64_t> primes;
+        for (auto &m : parms.coeff_modulus()) primes.push_back(m.value());
+        eng_ = detail::Engine::get(parms.poly_modulus_degree(), primes);
+        int K = eng_->K;
+        std::shared_ptr<ContextData> prev;
+        for (int limbs = K; limbs >= 1; --limbs) {   // key level, then the data levels
+            auto cd = std::make_shared<ContextData>();
+            EncryptionParameters p(parms.scheme());
+            p.set_poly_modulus_degree(parms.poly_modulus_degree());
+            p.set_coeff_modulus(std::vector<SmallModulus>(parms.coeff_modulus().begin(), parms.coeff_modulus().begin() + limbs));
+            cd->parms_ = p;
+            cd->id_ = detail::make_id(*eng_, limbs);
+            cd->chain_index_ = (std::size_t)(limbs == K ? K - 1 : limbs - 1);
+            int bits = 0;
+            // bit count of the product of the primes (SEAL: total_coeff_modulus_bit_count)
+            long double lg = 0;
+            for (int j = 0; j < limbs; j++) lg += std::log2((long double)eng_->primes[j]);
+            bits = (int)std::floor(lg) + 1;
+            cd->total_bits_ = bits;
+            if (prev) {
+                prev->next_ = cd;
+                cd->prev_ = prev;
+            }
+            data_[limbs] = cd;
+            prev = cd;
+        }
+    }
+    static std::shared_ptr<SEALContext> Create(const EncryptionParameters &parms, bool expand = true,
+                                               sec_level_type sec = sec_level_type::tc128) {
+        return std::make_shared<SEALContext>(parms, expand, sec);
+    }
+    std::shared_ptr<const ContextData> get_context_data(const parms_id_type &id) const {
+        auto it = data_.find((int)id[0]);
+        if (it == data_.end() || it->second->id_ != id) return nullptr;
+        return it->second;
+    }
+    std::shared_ptr<const ContextData> key_context_data() const { return data_.at(eng_->K); }
+    std::shared_ptr<const ContextData> first_context_data() const { return data_.at(eng_->K - 1); }
+    std::shared_ptr<const ContextData> last_context_data() const { return data_.at(1); }
+    const parms_id_type &key_parms_id() const { return key_context_data()->parms_id(); }
+    const parms_id_type &first_parms_id() const { return first_context_data()->parms_id(); }
+    const parms_id_type &last_parms_id() const { return last_context_data()->parms_id(); }
+    bool parameters_set() const { return true; }
+    const std::shared_ptr<detail::Engine> &engine() const { return eng_; }
+
+private:
+    std::shared_ptr<detail::Engine> eng_;
+    std::map<int, std::shared_ptr<ContextData>> data_;
+};
+
+namespace detail {
+inline std::shared_ptr<Engine> engine_of(const std::shared_ptr<SEALContext> &c) {
+    if (!c) throw std::invalid_argument("invalid context");
+    return c->engine();
+}
+inline std::shared_ptr<Engine> engine_of(const SEALContext &c) { return c.engine(); }
+}  // namespace detail
+
+// ------------------------------------------------------------------------------------ data objects
+class Plaintext {
+public:
+    Plaintext() = default;
+    double &scale() { return p_.scale; }
+    const double &scale() const { return p_.scale; }
+    parms_id_type parms_id() const { return p_.parms_id(); }
+    bool is_ntt_form() const { return true; }
+    std::size_t coeff_count() const { return p_.eng ? (std::size_t)p_.limbs * p_.eng->n : 0; }
+    detail::Poly &poly() { return p_; }
+    const detail::Poly &poly() const { return p_; }
+
+private:
+    detail::Poly p_;
+};
+
+class Ciphertext {
+public:
+    Ciphertext() = default;
+    double &scale() { return p_.scale; }
+    const double &scale() const { return p_.scale; }
+    parms_id_type parms_id() const { return p_.parms_id(); }
+    std::size_t size() const { return (std::size_t)p_.size; }
+    std::size_t coeff_mod_count() const { return (std::size_t)p_.limbs; }
+    std::size_t poly_modulus_degree() const { return p_.eng ? p_.eng->n : 0; }
+    bool is_ntt_form() const { return true; }
+    detail::Poly &poly() { return p_; }
+    const detail::Poly &poly() const { return p_; }
+
+private:
+    detail::Poly p_;
+};
+
+class SecretKey {
+public:
+    detail::BufPtr buf;   // [K][N], NTT form
+};
+class PublicKey {
+public:
+    detail::BufPtr buf;   // [2][K][N]
+};
+
+class KSwitchKeys {
+public:
+    struct Shared {
+        std::shared_ptr<detail::Engine> eng;
+        ckks_keyset *ks = nullptr;
+        std::map<std::uint64_t, detail::BufPtr> keys;   // Galois element (or 0 for relin) -> key
+        ~Shared() {
+            if (ks) ckks_keyset_destroy(ks);
+        }
+    };
+    std::shared_ptr<Shared> s;   // copies of RelinKeys / GaloisKeys share device storage
+    std::size_t size() const { return s ? s->keys.size() : 0; }
+};
+class RelinKeys : public KSwitchKeys {};
+class GaloisKeys : public KSwitchKeys {
+public:
+    bool has_key(std::uint64_t galois_elt) const { return s && s->keys.count(galois_elt); }
+    static std::size_t get_index(std::uint64_t galois_elt) { return (std::size_t)((galois_elt - 1) >> 1); }
+};
+
+// ------------------------------------------------------------------------------------ host-side ring helpers
+namespace detail {
+
+// thin wrappers: every ring operation goes through the GPU engine
+struct Ring {
+    std::shared_ptr<Engine> e;
+    std::mt19937_64 rng;
+    explicit Ring(std::shared_ptr<Engine> eng, std::uint64_t seed) : e(std::move(eng)), rng(seed) {}
+
+    ckks_view view(std::uint64_t *p, int batch, int size, int limbs) const {
+        ckks_view v;
+        v.data = p;
+        v.poly_stride = (std::uint64_t)limbs * e->n;
+        v.batch_stride = (std::uint64_t)size * limbs * e->n;
+        v.batch = batch;
+        v.size = size;
+        v.limbs = limbs;
+        v.reserved = 0;
+        return v;
+    }
+    // small signed polynomials [count][N] -> device [count][limbs][N] in NTT form
+    BufPtr small_to_ntt(const std::vector<int> &small, int count, int limbs) {
+        std::size_t n = e->n;
+        std::vector<std::uint64_t> h((std::size_t)count * limbs * n);
+        for (int c = 0; c < count; c++)
+            for (int j = 0; j < limbs; j++) {
+                std::uint64_t p = e->primes[j];
+                for (std::size_t q = 0; q < n; q++) {
+                    int v = small[(std::size_t)c * n + q];
+                    h[((std::size_t)c * limbs + j) * n + q] = v >= 0 ? (std::uint64_t)v : p - (std::uint64_t)(-v);
+                }
+            }
+        auto b = std::make_shared<DevBuf>(e, h.size());
+        check(ckks_upload(e->ctx, b->p, h.data(), h.size() * 8, nullptr));
+        check(ckks_stream_sync(e->ctx, nullptr));   // h goes out of scope
+        check(ckks_ntt_forward(e->ctx, b->p, count, limbs, 0, (std::uint64_t)limbs * n, nullptr));
+        return b;
+    }
+    std::vector<int> ternary(int count) {
+        std::vector<int> v((std::size_t)count * e->n);
+        std::uniform_int_distribution<int> d(-1, 1);
+        for (auto &x : v) x = d(rng);
+        return v;
+    }
+    std::vector<int> errors(int count) {   // sigma 3.2, clipped at 6 sigma (SEAL sample_poly_normal)
+        std::vector<int> v((std::size_t)count * e->n);
+        std::normal_distribution<double> d(0.0, 3.2);
+        for (auto &x : v) {
+            double z;
+            do z = d(rng);
+            while (std::fabs(z) > 19.2);
+            x = (int)std::lround(z);
+        }
+        return v;
+    }
+    BufPtr uniform(int count, int limbs) {
+        std::size_t n = e->n;
+        std::vector<std::uint64_t> h((std::size_t)count * limbs * n);
+        for (int c = 0; c < count; c++)
+            for (int j = 0; j < limbs; j++) {
+                std::uniform_int_distribution<std::uint64_t> d(0, e->primes[j] - 1);
+                for (std::size_t q = 0; q < n; q++) h[((std::size_t)c * limbs + j) * n + q] = d(rng);
+            }
+        auto b = std::make_shared<DevBuf>(e, h.size());
+        check(ckks_upload(e->ctx, b->p, h.data(), h.size() * 8, nullptr));
+        check(ckks_stream_sync(e->ctx, nullptr));
+        return b;
+    }
+    // count x (-(a s + e), a) over primes [0, limbs): device [count][2][limbs][N]
+    BufPtr enc_zero_sym(int count, const std::uint64_t *sk, int limbs) {
+        std::size_t n = e->n, pw = (std::size_t)limbs * n;
+        auto a = uniform(count, limbs);
+        auto err = small_to_ntt(errors(count), count, limbs);
+        auto out = std::make_shared<DevBuf>(e, (std::size_t)count * 2 * pw);
+        auto tmp = std::make_shared<DevBuf>(e, (std::size_t)count * pw);
+        ckks_view va = view(a->p, count, 1, limbs), vs = view(const_cast<std::uint64_t *>(sk), 1, 1, limbs);
+        vs.poly_stride = vs.batch_stride = (std::uint64_t)e->K * n;   // secret key rows are K limbs apart
+        ckks_view vt = view(tmp->p, count, 1, limbs), ve = view(err->p, count, 1, limbs);
+        check(ckks_multiply_plain(e->ctx, &va, &vs, &vt, nullptr));
+        check(ckks_add(e->ctx, &vt, &ve, &vt, nullptr));
+        check(ckks_negate(e->ctx, &vt, &vt, nullptr));
+        for (int c = 0; c < count; c++) {
+            check(ckks_copy(e->ctx, out->p + ((std::size_t)c * 2) * pw, tmp->p + (std::size_t)c * pw, pw * 8, nullptr));
+            check(ckks_copy(e->ctx, out->p + ((std::size_t)c * 2 + 1) * pw, a->p + (std::size_t)c * pw, pw * 8, nullptr));
+        }
+        return out;
+    }
+};
+
+}  // namespace detail
+
+// ------------------------------------------------------------------------------------ KeyGenerator
+class KeyGenerator {
+public:
+    template <class Ctx>
+    explicit KeyGenerator(const Ctx &context) : ring_(detail::engine_of(context), std::random_device{}()) {
+        auto &e = ring_.e;
+        sk_.buf = ring_.small_to_ntt(ring_.ternary(1), 1, e->K);
+    }
+    const SecretKey &secret_key() const { return sk_; }
+    PublicKey public_key() {
+        PublicKey pk;
+        pk.buf = ring_.enc_zero_sym(1, sk_.buf->p, ring_.e->K);
+        return pk;
+    }
+    void create_public_key(PublicKey &pk) { pk = public_key(); }
+
+    RelinKeys relin_keys() {
+        auto &e = ring_.e;
+        std::size_t kw = (std::size_t)e->K * e->n;
+        auto s2 = std::make_shared<detail::DevBuf>(e, kw);
+        ckks_view vs = ring_.view(sk_.buf->p, 1, 1, e->K), vo = ring_.view(s2->p, 1, 1, e->K);
+        detail::check(ckks_multiply_plain(e->ctx, &vs, &vs, &vo, nullptr));
+        RelinKeys rk;
+        rk.s = make_shared_keys();
+        rk.s->keys[0] = kswitch_key(s2->p);
+        detail::check(ckks_keyset_set_relin(rk.s->ks, rk.s->keys[0]->p));
+        return rk;
+    }
+    RelinKeys relin_keys_local() { return relin_keys(); }
+    void create_relin_keys(RelinKeys &rk) { rk = relin_keys(); }
+
+    // default: steps +-2^i and the conjugation (SEAL KeyGenerator::galois_keys())
+    GaloisKeys galois_keys() {
+        auto &e = ring_.e;
+        std::vector<std::uint64_t> elts = {2 * (std::uint64_t)e->n - 1};
+        for (int i = 0; i < e->log_n - 1; i++) {
+            elts.push_back(ckks_galois_elt_from_step(e->ctx, 1 << i));
+            elts.push_back(ckks_galois_elt_from_step(e->ctx, -(1 << i)));
+        }
+        return galois_keys(elts);
+    }
+    GaloisKeys galois_keys(const std::vector<int> &steps) {
+        std::vector<std::uint64_t> elts;
+        for (int s : steps) {
+            std::uint64_t g = ckks_galois_elt_from_step(ring_.e->ctx, s);
+            if (!g) throw std::invalid_argument("step count too large");
+            elts.push_back(g);
+        }
+        return galois_keys(elts);
+    }
+    GaloisKeys galois_keys(const std::vector<std::uint64_t> &elts) {
+        auto &e = ring_.e;
+        GaloisKeys gk;
+        gk.s = make_shared_keys();
+        std::size_t n = e->n;
+        std::vector<std::uint64_t> hsk((std::size_t)e->K * n), perm_sk(hsk.size());
+        detail::check(ckks_download(e->ctx, hsk.data(), sk_.buf->p, hsk.size() * 8, nullptr));
+        detail::check(ckks_stream_sync(e->ctx, nullptr));
+        for (std::uint64_t g : elts) {
+            if (gk.s->keys.count(g)) continue;
+            // sigma_g(s) in NTT form is a permutation of s (SEAL apply_galois_ntt)
+            for (std::size_t i = 0; i < n; i++) {
+                std::uint64_t ex = (g * (2ull * detail::bitrev((std::uint32_t)i, e->log_n) + 1)) & (2 * n - 1);
+                std::size_t src = detail::bitrev((std::uint32_t)((ex - 1) >> 1), e->log_n);
+                for (int j = 0; j < e->K; j++) perm_sk[(std::size_t)j * n + i] = hsk[(std::size_t)j * n + src];
+            }
+            auto d = std::make_shared<detail::DevBuf>(e, perm_sk.size());
+            detail::check(ckks_upload(e->ctx, d->p, perm_sk.data(), perm_sk.size() * 8, nullptr));
+            detail::check(ckks_stream_sync(e->ctx, nullptr));
+            gk.s->keys[g] = kswitch_key(d->p);
+            detail::check(ckks_keyset_set_galois(gk.s->ks, g, gk.s->keys[g]->p));
+        }
+        return gk;
+    }
+    void create_galois_keys(GaloisKeys &gk) { gk = galois_keys(); }
+    void create_galois_keys(const std::vector<int> &steps, GaloisKeys &gk) { gk = galois_keys(steps); }
+
+private:
+    std::shared_ptr<KSwitchKeys::Shared> make_shared_keys() {
+        auto s = std::make_shared<KSwitchKeys::Shared>();
+        s->eng = ring_.e;
+        detail::check(ckks_keyset_create(ring_.e->ctx, &s->ks));
+        return s;
+    }
+    // SEAL generate_one_kswitch_key: digit i = Enc(0) with (P mod q_i) new_key in limb i
+    detail::BufPtr kswitch_key(const std::uint64_t *new_key) {
+        auto &e = ring_.e;
+        int K = e->K;
+        std::size_t n = e->n, kw = (std::size_t)K * n;
+        auto key = ring_.enc_zero_sym(K - 1, sk_.buf->p, K);   // [K-1][2][K][N]
+        std::vector<std::uint64_t> fac(kw);
+        for (int j = 0; j < K; j++)
+            for (std::size_t q = 0; q < n; q++) fac[(std::size_t)j * n + q] = e->primes[K - 1] % e->primes[j];
+        auto dfac = std::make_shared<detail::DevBuf>(e, kw), scaled = std::make_shared<detail::DevBuf>(e, kw);
+        detail::check(ckks_upload(e->ctx, dfac->p, fac.data(), kw * 8, nullptr));
+        detail::check(ckks_stream_sync(e->ctx, nullptr));
+        ckks_view vn = ring_.view(const_cast<std::uint64_t *>(new_key), 1, 1, K), vf = ring_.view(dfac->p, 1, 1, K),
+                  vsc = ring_.view(scaled->p, 1, 1, K);
+        detail::check(ckks_multiply_plain(e->ctx, &vn, &vf, &vsc, nullptr));
+        // add limb i of `scaled` into limb i of component 0 of digit i: done as a full-width add of a
+        // one-hot limb selection, i.e. K-1 single-limb adds expressed through per-limb views
+        for (int i = 0; i < K - 1; i++) {
+            // a (i+1)-limb view whose only touched limb is i would still add limbs < i, so use the NTT-free
+            // route: copy limb i of scaled into a zeroed K-limb poly and add it
+            auto z = std::make_shared<detail::DevBuf>(e, kw);
+            std::vector<std::uint64_t> zeros(kw, 0);
+            detail::check(ckks_upload(e->ctx, z->p, zeros.data(), kw * 8, nullptr));
+            detail::check(ckks_stream_sync(e->ctx, nullptr));
+            detail::check(ckks_copy(e->ctx, z->p + (std::size_t)i * n, scaled->p + (std::size_t)i * n, n * 8, nullptr));
+            std::uint64_t *c0 = key->p + ((std::size_t)i * 2) * kw;
+            ckks_view vc = ring_.view(c0, 1, 1, K), vz = ring_.view(z->p, 1, 1, K);
+            detail::check(ckks_add(e->ctx, &vc, &vz, &vc, nullptr));
+        }
+        return key;
+    }
+    detail::Ring ring_;
+    SecretKey sk_;
+};
+
+// ------------------------------------------------------------------------------------ CKKSEncoder
+class CKKSEncoder {
+public:
+    template <class Ctx>
+    explicit CKKSEncoder(const Ctx &context) : e_(detail::engine_of(context)) {
+        std::size_t n = e_->n, slots = n / 2;
+        pos_.resize(n);
+        std::uint64_t v = 1;
+        for (std::size_t i = 0; i < slots; i++) {
+            pos_[i] = detail::bitrev((std::uint32_t)((v - 1) >> 1), e_->log_n);
+            pos_[slots + i] = detail::bitrev((std::uint32_t)((2 * n - v - 1) >> 1), e_->log_n);
+            v = v * 3 % (2 * n);
+        }
+        roots_.resize(n);
+        const double pi = std::acos(-1.0);
+        for (std::size_t i = 0; i < n; i++) {
+            double ang = 2.0 * pi * (double)detail::bitrev((std::uint32_t)i, e_->log_n) / (double)(2 * n);
+            roots_[i] = std::complex<double>(std::cos(ang), std::sin(ang));
+        }
+    }
+    std::size_t slot_count() const { return e_->n / 2; }
+
+    void encode(const std::vector<double> &values, parms_id_type id, double scale, Plaintext &dst, MemoryPoolHandle = {}) {
+        encode_impl(values, (int)id[0], scale, dst);
+    }
+    void encode(const std::vector<double> &values, double scale, Plaintext &dst, MemoryPoolHandle = {}) {
+        encode_impl(values, e_->K - 1, scale, dst);
+    }
+    void encode(double value, parms_id_type id, double scale, Plaintext &dst, MemoryPoolHandle = {}) {
+        encode_const(value, (int)id[0], scale, dst);
+    }
+    void encode(double value, double scale, Plaintext &dst, MemoryPoolHandle = {}) { encode_const(value, e_->K - 1, scale, dst); }
+
+    void decode(const Plaintext &plain, std::vector<double> &out, MemoryPoolHandle = {}) {
+        const detail::Poly &p = plain.poly();
+        if (!p.buf) throw std::invalid_argument("plain is not valid for encryption parameters");
+        std::size_t n = e_->n, slots = n / 2;
+        int L = p.limbs;
+        auto tmp = std::make_shared<detail::DevBuf>(e_, (std::size_t)L * n);
+        detail::check(ckks_copy(e_->ctx, tmp->p, p.buf->p, (std::size_t)L * n * 8, nullptr));
+        detail::check(ckks_ntt_inverse(e_->ctx, tmp->p, 1, L, 0, (std::uint64_t)L * n, nullptr));
+        std::vector<std::uint64_t> h((std::size_t)L * n);
+        detail::check(ckks_download(e_->ctx, h.data(), tmp->p, h.size() * 8, nullptr));
+        detail::check(ckks_stream_sync(e_->ctx, nullptr));
+        // CRT composition by Garner's mixed-radix digits, centred, as long double
+        std::vector<std::uint64_t> inv(L);
+        std::vector<long double> radix(L);
+        for (int k = 0; k < L; k++) {
+            std::uint64_t pk = e_->primes[k], prod = 1 % pk;
+            for (int i = 0; i < k; i++) prod = detail::mulmod(prod, e_->primes[i] % pk, pk);
+            inv[k] = detail::powmod(prod, pk - 2, pk);
+            radix[k] = k ? radix[k - 1] * (long double)e_->primes[k - 1] : 1.0L;
+        }
+        std::vector<std::complex<double>> vals(n);
+        std::vector<std::uint64_t> dg(L);
+        for (std::size_t q = 0; q < n; q++) {
+            for (int k = 0; k < L; k++) {
+                std::uint64_t pk = e_->primes[k], acc = 0, mult = 1 % pk;
+                for (int i = 0; i < k; i++) {
+                    acc = (acc + detail::mulmod(dg[i] % pk, mult, pk)) % pk;
+                    mult = detail::mulmod(mult, e_->primes[i] % pk, pk);
+                }
+                std::uint64_t x = h[(std::size_t)k * n + q];
+                dg[k] = detail::mulmod((x + pk - acc) % pk, inv[k], pk);
+            }
+            bool neg = dg[L - 1] >= (e_->primes[L - 1] + 1) / 2;
+            if (neg) {
+                for (int k = 0; k < L; k++) dg[k] = e_->primes[k] - 1 - dg[k];
+                for (int k = 0; k < L; k++) {
+                    if (++dg[k] < e_->primes[k]) break;
+                    dg[k] = 0;
+                }
+            }
+            long double v = 0;
+            for (int k = L - 1; k >= 0; k--) v += (long double)dg[k] * radix[k];
+            vals[q] = std::complex<double>((double)((neg ? -v : v) / (long double)p.scale), 0.0);
+        }
+        // forward negacyclic FFT (same butterfly structure as the NTT, zeta for psi)
+        std::size_t t = n >> 1;
+        for (std::size_t m = 1; m < n; m <<= 1, t >>= 1)
+            for (std::size_t i = 0; i < m; i++) {
+                std::complex<double> w = roots_[m + i];
+                for (std::size_t k = 2 * i * t; k < 2 * i * t + t; k++) {
+                    std::complex<double> u = vals[k], x = vals[k + t] * w;
+                    vals[k] = u + x;
+                    vals[k + t] = u - x;
+                }
+            }
+        out.resize(slots);
+        for (std::size_t i = 0; i < slots; i++) out[i] = vals[pos_[i]].real();
+    }
+
+private:
+    void finish(const std::vector<long double> &coeffs, int limbs, double scale, Plaintext &dst) {
+        std::size_t n = e_->n;
+        if (limbs < 1 || limbs > e_->K - 1) throw std::invalid_argument("parms_id is not valid for encryption parameters");
+        if (scale <= 0) throw std::invalid_argument("scale out of bounds");
+        std::vector<std::uint64_t> h((std::size_t)limbs * n);
+        for (std::size_t q = 0; q < n; q++) {
+            long double c = std::roundl(coeffs[q]);
+            bool neg = c < 0;
+            long double a = neg ? -c : c;
+            if (a >= 0x1p126L) throw std::invalid_argument("encoded values are too large");
+            detail::u128 mag = (detail::u128)a;
+            for (int j = 0; j < limbs; j++) {
+                std::uint64_t p = e_->primes[j], r = (std::uint64_t)(mag % p);
+                h[(std::size_t)j * n + q] = (neg && r) ? p - r : r;
+            }
+        }
+        detail::Poly &p = dst.poly();
+        p.allocate(e_, 1, limbs);
+        p.scale = scale;
+        detail::check(ckks_upload(e_->ctx, p.buf->p, h.data(), h.size() * 8, nullptr));
+        detail::check(ckks_stream_sync(e_->ctx, nullptr));
+    }
+    void encode_impl(const std::vector<double> &values, int limbs, double scale, Plaintext &dst) {
+        std::size_t n = e_->n, slots = n / 2;
+        if (values.size() > slots) throw std::invalid_argument("values has invalid size");
+        std::vector<std::complex<double>> v(n);
+        for (std::size_t i = 0; i < values.size(); i++) {
+            v[pos_[i]] = values[i];
+            v[pos_[slots + i]] = values[i];
+        }
+        // inverse negacyclic FFT (Gentleman-Sande with conjugate roots), then 1/N
+        std::size_t t = 1;
+        for (std::size_t m = n >> 1; m >= 1; m >>= 1, t <<= 1)
+            for (std::size_t i = 0; i < m; i++) {
+                std::complex<double> w = std::conj(roots_[m + i]);
+                for (std::size_t k = 2 * i * t; k < 2 * i * t + t; k++) {
+                    std::complex<double> u = v[k], x = v[k + t];
+                    v[k] = u + x;
+                    v[k + t] = (u - x) * w;
+                }
+            }
+        std::vector<long double> coeffs(n);
+        for (std::size_t q = 0; q < n; q++) coeffs[q] = (long double)(v[q].real() / (double)n) * (long double)scale;
+        finish(coeffs, limbs, scale, dst);
+        detail::Poly &p = dst.poly();
+        detail::check(ckks_ntt_forward(e_->ctx, p.buf->p, 1, limbs, 0, (std::uint64_t)limbs * n, nullptr));
+    }
+    void encode_const(double value, int limbs, double scale, Plaintext &dst) {
+        // constant polynomial round(value * scale); its NTT is that constant in every position
+        std::vector<long double> coeffs(e_->n, (long double)value * (long double)scale);
+        finish(coeffs, limbs, scale, dst);
+    }
+    std::shared_ptr<detail::Engine> e_;
+    std::vector<std::uint32_t> pos_;
+    std::vector<std::complex<double>> roots_;
+};
+
+// ------------------------------------------------------------------------------------ Encryptor / Decryptor
+class Encryptor {
+public:
+    template <class Ctx>
+    Encryptor(const Ctx &context, const PublicKey &pk) : ring_(detail::engine_of(context), std::random_device{}()), pk_(pk) {}
+
+    // (u pk + e) one level above the plaintext's level, divided-and-rounded by the extra prime
+    // (the rescale kernels), plus the plaintext in c0
+    void encrypt(const Plaintext &plain, Ciphertext &dst, MemoryPoolHandle = {}) {
+        auto &e = ring_.e;
+        const detail::Poly &pt = plain.poly();
+        if (!pt.buf) throw std::invalid_argument("plain is not valid for encryption parameters");
+        std::size_t n = e->n;
+        int L = pt.limbs, W = L + 1, K = e->K;
+        auto u = ring_.small_to_ntt(ring_.ternary(1), 1, W);
+        auto big = std::make_shared<detail::DevBuf>(e, (std::size_t)2 * W * n);
+        for (int k = 0; k < 2; k++) {
+            auto err = ring_.small_to_ntt(ring_.errors(1), 1, W);
+            ckks_view vu = ring_.view(u->p, 1, 1, W), ve = ring_.view(err->p, 1, 1, W);
+            ckks_view vpk = ring_.view(pk_.buf->p + (std::size_t)k * K * n, 1, 1, W);
+            ckks_view vo = ring_.view(big->p + (std::size_t)k * W * n, 1, 1, W);
+            detail::check(ckks_multiply_plain(e->ctx, &vu, &vpk, &vo, nullptr));
+            detail::check(ckks_add(e->ctx, &vo, &ve, &vo, nullptr));
+        }
+        detail::Poly out;
+        out.allocate(e, 2, L);
+        out.scale = pt.scale;
+        ckks_view vin = ring_.view(big->p, 1, 2, W), vout = out.view(), vpt = pt.view();
+        detail::check(ckks_rescale(e->ctx, &vin, &vout, nullptr));
+        detail::check(ckks_add_plain(e->ctx, &vout, &vpt, &vout, nullptr));
+        dst.poly() = out;
+    }
+
+private:
+    detail::Ring ring_;
+    PublicKey pk_;
+};
+
+class Decryptor {
+public:
+    template <class Ctx>
+    Decryptor(const Ctx &context, const SecretKey &sk) : ring_(detail::engine_of(context), 0), sk_(sk) {}
+
+    void decrypt(const Ciphertext &encrypted, Plaintext &dst) {
+        auto &e = ring_.e;
+        const detail::Poly &ct = encrypted.poly();
+        if (!ct.buf) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        std::size_t n = e->n;
+        int L = ct.limbs, S = ct.size;
+        detail::Poly out;
+        out.allocate(e, 1, L);
+        out.scale = ct.scale;
+        ckks_view vs = ring_.view(sk_.buf->p, 1, 1, L);
+        vs.poly_stride = vs.batch_stride = (std::uint64_t)e->K * n;
+        ckks_view vo = out.view();
+        auto poly_view = [&](int k) {
+            ckks_view v = ct.view();
+            v.data += (std::uint64_t)k * v.poly_stride;
+            v.size = 1;
+            return v;
+        };
+        ckks_view top = poly_view(S - 1);
+        // Horner in s: acc = c_{S-1}; acc = acc * s + c_k
+        ckks_view vt = top;
+        for (int k = S - 2; k >= 0; k--) {
+            detail::check(ckks_multiply_plain(e->ctx, &vt, &vs, &vo, nullptr));
+            ckks_view vk = poly_view(k);
+            detail::check(ckks_add(e->ctx, &vo, &vk, &vo, nullptr));
+            vt = vo;
+        }
+        if (S == 1) detail::check(ckks_copy(e->ctx, vo.data, top.data, (std::size_t)L * n * 8, nullptr));
+        dst.poly() = out;
+    }
+
+private:
+    detail::Ring ring_;
+    SecretKey sk_;
+};
+
+// ------------------------------------------------------------------------------------ Evaluator
+class Evaluator {
+public:
+    template <class Ctx>
+    explicit Evaluator(const Ctx &context) : e_(detail::engine_of(context)) {}
+
+    // ---- add / sub / negate (helper.h:247,259,484; logistic_regression_ckks.cpp:288,341-342)
+    void add_inplace(Ciphertext &a, const Ciphertext &b) { binary(a, b, a, 0); }
+    void add(const Ciphertext &a, const Ciphertext &b, Ciphertext &dst) { binary(a, b, dst, 0); }
+    void sub_inplace(Ciphertext &a, const Ciphertext &b) { binary(a, b, a, 1); }
+    void sub(const Ciphertext &a, const Ciphertext &b, Ciphertext &dst) { binary(a, b, dst, 1); }
+    void negate_inplace(Ciphertext &a) {
+        a.poly().make_unique();
+        ckks_view v = a.poly().view();
+        detail::check(ckks_negate(e_->ctx, &v, &v, nullptr));
+    }
+    void negate(const Ciphertext &a, Ciphertext &dst) {
+        dst = a;
+        negate_inplace(dst);
+    }
+    void add_many(const std::vector<Ciphertext> &cts, Ciphertext &dst) {
+        if (cts.empty()) throw std::invalid_argument("encrypteds cannot be empty");
+        Ciphertext acc = cts[0];
+        for (std::size_t i = 1; i < cts.size(); i++) add_inplace(acc, cts[i]);
+        dst = acc;
+    }
+
+    // ---- multiply (helper.h:222,432; matrix_multiplication.cpp:105,126)
+    void multiply(const Ciphertext &a, const Ciphertext &b, Ciphertext &dst, MemoryPoolHandle = {}) {
+        const detail::Poly &pa = a.poly(), &pb = b.poly();
+        need(pa), need(pb);
+        if (pa.limbs != pb.limbs) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+        double scale = pa.scale * pb.scale;
+        scale_ok(scale, pa.limbs);
+        detail::Poly out;
+        out.allocate(e_, pa.size + pb.size - 1, pa.limbs);
+        out.scale = scale;
+        ckks_view va = pa.view(), vb = pb.view(), vo = out.view();
+        detail::check(ckks_multiply(e_->ctx, &va, &vb, &vo, nullptr));
+        dst.poly() = out;
+    }
+    void multiply_inplace(Ciphertext &a, const Ciphertext &b, MemoryPoolHandle = {}) { multiply(a, b, a); }
+    void square(const Ciphertext &a, Ciphertext &dst, MemoryPoolHandle = {}) { multiply(a, a, dst); }
+    void square_inplace(Ciphertext &a, MemoryPoolHandle = {}) { multiply(a, a, a); }
+
+    // ---- plaintext ops (helper.h:250,256,271; logistic_regression_ckks.cpp:198)
+    void multiply_plain(const Ciphertext &a, const Plaintext &p, Ciphertext &dst, MemoryPoolHandle = {}) {
+        const detail::Poly &pa = a.poly(), &pp = p.poly();
+        need(pa), need(pp);
+        if (pa.limbs != pp.limbs) throw std::invalid_argument("encrypted and plain parameter mismatch");
+        double scale = pa.scale * pp.scale;
+        scale_ok(scale, pa.limbs);
+        detail::Poly out;
+        out.allocate(e_, pa.size, pa.limbs);
+        out.scale = scale;
+        ckks_view va = pa.view(), vp = pp.view(), vo = out.view();
+        detail::check(ckks_multiply_plain(e_->ctx, &va, &vp, &vo, nullptr));
+        transparent_check(out);
+        dst.poly() = out;
+    }
+    void multiply_plain_inplace(Ciphertext &a, const Plaintext &p, MemoryPoolHandle = {}) { multiply_plain(a, p, a); }
+    void add_plain(const Ciphertext &a, const Plaintext &p, Ciphertext &dst) {
+        const detail::Poly &pa = a.poly(), &pp = p.poly();
+        need(pa), need(pp);
+        if (pa.limbs != pp.limbs) throw std::invalid_argument("encrypted and plain parameter mismatch");
+        if (pa.scale != pp.scale) throw std::invalid_argument("scale mismatch");
+        detail::Poly out;
+        out.allocate(e_, pa.size, pa.limbs);
+        out.scale = pa.scale;
+        ckks_view va = pa.view(), vp = pp.view(), vo = out.view();
+        detail::check(ckks_add_plain(e_->ctx, &va, &vp, &vo, nullptr));
+        dst.poly() = out;
+    }
+    void add_plain_inplace(Ciphertext &a, const Plaintext &p) { add_plain(a, p, a); }
+
+    // ---- key switching (helper.h:440,541; every rotate_vector call)
+    void relinearize_inplace(Ciphertext &a, const RelinKeys &rk, MemoryPoolHandle = {}) { relinearize(a, rk, a); }
+    void relinearize(const Ciphertext &a, const RelinKeys &rk, Ciphertext &dst, MemoryPoolHandle = {}) {
+        const detail::Poly &pa = a.poly();
+        need(pa);
+        if (pa.size == 2) {   // SEAL: nothing to do
+            dst = a;
+            return;
+        }
+        if (!rk.s || !rk.s->keys.count(0)) throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+        detail::Poly out;
+        out.allocate(e_, 2, pa.limbs);
+        out.scale = pa.scale;
+        ckks_view va = pa.view(), vo = out.view();
+        detail::check(ckks_relinearize(e_->ctx, &va, rk.s->keys.at(0)->p, &vo, nullptr));
+        dst.poly() = out;
+    }
+    void rotate_vector(const Ciphertext &a, int steps, const GaloisKeys &gk, Ciphertext &dst, MemoryPoolHandle = {}) {
+        const detail::Poly &pa = a.poly();
+        need(pa);
+        if (!gk.s) throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+        if (pa.size > 2) throw std::invalid_argument("encrypted size must be 2");
+        detail::Poly out, scratch;
+        out.allocate(e_, 2, pa.limbs);
+        scratch.allocate(e_, 2, pa.limbs);
+        out.scale = pa.scale;
+        ckks_view va = pa.view(), vo = out.view(), vs = scratch.view();
+        detail::check(ckks_rotate(e_->ctx, gk.s->ks, &va, steps, &vo, &vs, nullptr));
+        dst.poly() = out;
+    }
+    void rotate_vector_inplace(Ciphertext &a, int steps, const GaloisKeys &gk, MemoryPoolHandle = {}) {
+        rotate_vector(a, steps, gk, a);
+    }
+    void apply_galois(const Ciphertext &a, std::uint64_t galois_elt, const GaloisKeys &gk, Ciphertext &dst, MemoryPoolHandle = {}) {
+        const detail::Poly &pa = a.poly();
+        need(pa);
+        if (!gk.has_key(galois_elt)) throw std::invalid_argument("Galois key not present");
+        detail::Poly out;
+        out.allocate(e_, 2, pa.limbs);
+        out.scale = pa.scale;
+        ckks_view va = pa.view(), vo = out.view();
+        detail::check(ckks_apply_galois(e_->ctx, &va, galois_elt, gk.s->keys.at(galois_elt)->p, &vo, nullptr));
+        dst.poly() = out;
+    }
+    void apply_galois_inplace(Ciphertext &a, std::uint64_t galois_elt, const GaloisKeys &gk, MemoryPoolHandle = {}) {
+        apply_galois(a, galois_elt, gk, a);
+    }
+
+    // ---- rescale / mod switch (helper.h:441,536,543; matrix_multiplication.cpp:71-72,112)
+    void rescale_to_next(const Ciphertext &a, Ciphertext &dst, MemoryPoolHandle = {}) {
+        const detail::Poly &pa = a.poly();
+        need(pa);
+        if (pa.limbs < 2) throw std::invalid_argument("end of modulus switching chain reached");
+        detail::Poly out;
+        out.allocate(e_, pa.size, pa.limbs - 1);
+        out.scale = pa.scale / (double)e_->primes[pa.limbs - 1];
+        ckks_view va = pa.view(), vo = out.view();
+        detail::check(ckks_rescale(e_->ctx, &va, &vo, nullptr));
+        dst.poly() = out;
+    }
+    void rescale_to_next_inplace(Ciphertext &a, MemoryPoolHandle = {}) { rescale_to_next(a, a); }
+    void mod_switch_to_next_inplace(Ciphertext &a, MemoryPoolHandle = {}) { drop(a.poly(), a.poly().limbs - 1); }
+    void mod_switch_to_next_inplace(Plaintext &p) { drop(p.poly(), p.poly().limbs - 1); }
+    void mod_switch_to_next(const Ciphertext &a, Ciphertext &dst, MemoryPoolHandle = {}) {
+        dst = a;
+        mod_switch_to_next_inplace(dst);
+    }
+    void mod_switch_to_next(const Plaintext &a, Plaintext &dst) {
+        dst = a;
+        mod_switch_to_next_inplace(dst);
+    }
+    void mod_switch_to_inplace(Ciphertext &a, parms_id_type id, MemoryPoolHandle = {}) { drop(a.poly(), (int)id[0]); }
+    void mod_switch_to_inplace(Plaintext &p, parms_id_type id) { drop(p.poly(), (int)id[0]); }
+    void mod_switch_to(const Ciphertext &a, parms_id_type id, Ciphertext &dst, MemoryPoolHandle = {}) {
+        dst = a;
+        mod_switch_to_inplace(dst, id);
+    }
+
+private:
+    static void need(const detail::Poly &p) {
+        if (!p.buf) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    }
+    void scale_ok(double scale, int limbs) const {
+        long double lg = 0;
+        for (int j = 0; j < limbs; j++) lg += std::log2((long double)e_->primes[j]);
+        int bits = (int)std::floor(lg) + 1;
+        if (scale <= 0 || (int)std::log2(scale) >= bits) throw std::invalid_argument("scale out of bounds");
+    }
+    void transparent_check(const detail::Poly &p) {
+        auto flag = std::make_shared<detail::DevBuf>(e_, 2);
+        ckks_view v = p.view();
+        detail::check(ckks_is_transparent(e_->ctx, &v, (std::int32_t *)flag->p, nullptr));
+        std::int32_t h = 0;
+        detail::check(ckks_download(e_->ctx, &h, flag->p, 4, nullptr));
+        detail::check(ckks_stream_sync(e_->ctx, nullptr));
+        if (h) throw std::logic_error("result ciphertext is transparent");
+    }
+    // CKKS mod-switch: the last limbs are simply dropped; with a fixed limb capacity this is metadata
+    void drop(detail::Poly &p, int limbs) {
+        need(p);
+        if (limbs == p.limbs) return;
+        if (limbs > p.limbs || limbs < 1) {
+            if (p.limbs < 2 && limbs < 1) throw std::invalid_argument("end of modulus switching chain reached");
+            throw std::invalid_argument("cannot switch to higher level modulus");
+        }
+        p.limbs = limbs;
+    }
+    void binary(const Ciphertext &a, const Ciphertext &b, Ciphertext &dst, int op) {
+        const detail::Poly &pa = a.poly(), &pb = b.poly();
+        need(pa), need(pb);
+        if (pa.limbs != pb.limbs) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+        if (pa.scale != pb.scale) throw std::invalid_argument("scale mismatch");
+        int S = std::max(pa.size, pb.size);
+        detail::Poly out;
+        out.allocate(e_, S, pa.limbs);
+        out.scale = pa.scale;
+        // SEAL allows different sizes: the common polys are combined, the rest copied (negated for sub)
+        int common = std::min(pa.size, pb.size);
+        ckks_view va = pa.view(), vb = pb.view(), vo = out.view();
+        va.size = vb.size = vo.size = common;
+        detail::check(op == 0 ? ckks_add(e_->ctx, &va, &vb, &vo, nullptr) : ckks_sub(e_->ctx, &va, &vb, &vo, nullptr));
+        if (S > common) {
+            const detail::Poly &big = pa.size > pb.size ? pa : pb;
+            ckks_view vbg = big.view(), vt = out.view();
+            vbg.data += (std::uint64_t)common * vbg.poly_stride;
+            vt.data += (std::uint64_t)common * vt.poly_stride;
+            vbg.size = vt.size = S - common;
+            if (op == 1 && pb.size > pa.size) detail::check(ckks_negate(e_->ctx, &vbg, &vt, nullptr));
+            else detail::check(copy_polys(e_->ctx, &vbg, &vt));
+        }
+        dst.poly() = out;
+    }
+    static int copy_polys(ckks_ctx *ctx, const ckks_view *src, const ckks_view *dst) {
+        std::size_t n = (std::size_t)1 << ckks_ctx_log_n(ctx);
+        for (int s = 0; s < src->size; s++) {
+            int rc = ckks_copy(ctx, dst->data + (std::uint64_t)s * dst->poly_stride, src->data + (std::uint64_t)s * src->poly_stride,
+                               (std::size_t)src->limbs * n * 8, nullptr);
+            if (rc) return rc;
+        }
+        return CKKS_OK;
+    }
+    std::shared_ptr<detail::Engine> e_;
+};
+
+}  // namespace seal

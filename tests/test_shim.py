@@ -1,0 +1,55 @@
+"""The C++ drop-in boundary: seal/seal.h over libckks_b200.so.
+CPU: the reference's own hot-path sources compile and link UNCHANGED against the shim (only where
+/root/reference exists -- it does not travel to the GPU box).  GPU: a driver written the way the
+reference writes its programs runs end to end through the shim."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "seal-fyp-logistic-regression_b200")
+LIB = os.path.join(PKG_DIR, "libckks_b200.so")
+INC = ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG_DIR, "include")]
+REF = "/root/reference"
+DRIVER = os.path.join(ROOT, "tests", "cpp", "shim_driver")
+
+HOT_PATH_FILES = ["linear_transformation.cpp", "linear_transformation2.cpp", "polynomial.cpp",
+                  "logistic_regression_ckks.cpp", "matrix_transpose.cpp", "matrix_multiplication.cpp",
+                  "matrix_mult_benchmark.cpp", "4_ckks.cpp", "benchmark.cpp"]
+
+
+def build_driver():
+    src = os.path.join(ROOT, "tests", "cpp", "shim_driver.cpp")
+    hdr = os.path.join(PKG_DIR, "include", "seal", "seal.h")
+    if os.path.exists(DRIVER) and all(os.path.getmtime(DRIVER) >= os.path.getmtime(f) for f in (src, hdr, LIB)):
+        return DRIVER
+    subprocess.check_call(["g++", "-std=c++17", "-O2"] + INC + [src, "-o", DRIVER, LIB,
+                                                              "-Wl,-rpath," + PKG_DIR])
+    return DRIVER
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources are only present in the build container")
+@pytest.mark.parametrize("name", HOT_PATH_FILES)
+def test_reference_sources_build_unchanged(pkg, name, tmp_path):
+    """`those files link against it unchanged` (BASELINE.json north_star): compile + link, no edits"""
+    out = str(tmp_path / "a.out")
+    res = subprocess.run(["g++", "-std=c++17", "-w", "-O0"] + INC + ["-I", REF, os.path.join(REF, name), "-o", out, LIB,
+                                                                    "-Wl,-rpath," + PKG_DIR],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout[-3000:]
+
+
+def test_shim_driver_builds(pkg):
+    build_driver()
+    assert os.path.exists(DRIVER)
+
+
+@pytest.mark.gpu
+def test_shim_driver_runs_on_gpu(pkg):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    exe = build_driver()
+    res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-3000:]
