@@ -31,12 +31,14 @@ g = ctx.galois_elt(1)
 for _ in range(3):
     ev.apply_galois(a, g, keys, out=b)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()          # ncu --profile-from-start off captures only this region
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
     ev.apply_galois(a, g, keys, out=b)
 e1.record()
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 ms = e0.elapsed_time(e1) / reps
 alg = batch * (2 * L * L + 6 * L) * 8 * ctx.n
 print("N=%d L=%d batch=%d: %.1f us per batched key switch, %.0f ks/s, %.0f GB/s algorithmic" % (

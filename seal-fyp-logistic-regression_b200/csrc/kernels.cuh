@@ -79,9 +79,9 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_col(DView src, DView dst, i
     u64 x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[col_coarse_idx<LOGN>(c0, e)];
-    fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m.p, m.p2, smem);
+    fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, smem);
 #pragma unroll
-    for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];  // lazy [0,4p)
+    for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];  // lazy
 }
 
 template <int LOGN>
@@ -96,9 +96,9 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_row(DView src, DView dst, i
     u64 x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
-    fwd_row_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m.p, m.p2, t0, smem);
+    fwd_row_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, t0, smem);
 #pragma unroll
-    for (int e = 0; e < 8; e++) out[t0 + row_contig_li(e)] = csub(csub(x[e], m.p2), m.p);
+    for (int e = 0; e < 8; e++) out[t0 + row_contig_li(e)] = reduce64(x[e], m);
 }
 
 template <int LOGN>
@@ -113,9 +113,9 @@ __global__ void __launch_bounds__(NTT_THREADS) k_inv_row(DView src, DView dst, i
     u64 x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_contig_li(e)];
-    inv_row_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m.p, m.p2, t0, smem);
+    inv_row_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m, t0, smem);
 #pragma unroll
-    for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = x[e];  // lazy [0,2p)
+    for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = x[e];  // lazy
 }
 
 // ADD_HALF: store (v + (p >> 1)) mod p instead of v -- the "flooring to rounding" step of SEAL's
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_inv_col(DView src, DView dst, i
     const u64 half = (ADD_HALF && t.round_half) ? (m.p >> 1) : 0;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-        u64 v = csub(x[e], m.p);
+        u64 v = csub(csub(x[e], m.p2), m.p);
         if (ADD_HALF) v = csub(v + half, m.p);
         out[col_coarse_idx<LOGN>(c0, e)] = v;
     }
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ks_intt_row(KsRoute rt, u64 *D,
         int g = t0 + row_contig_li(e);
         x[e] = in[GALOIS ? perm[g] : g];
     }
-    inv_row_pass<LOGN>(x, t.twi + (size_t)i * G::N, m.p, m.p2, t0, smem);
+    inv_row_pass<LOGN>(x, t.twi + (size_t)i * G::N, m, t0, smem);
 #pragma unroll
     for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = x[e];
 }
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ks_modup_col(const u64 *__restr
     u64 x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = reduce64(in[col_coarse_idx<LOGN>(c0, e)], m);
-    fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m.p, m.p2, smem);
+    fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, smem);
 #pragma unroll
     for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
 }
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ks_modup_col(const u64 *__restr
 //     acc_k = sum_i NTT_pj(digit_i) (.) ksk[i][k][pj]     (k = 0,1), 128-bit lazy sums,
 // one Barrett reduction at the end.  Key limbs stream once from HBM, fully coalesced.
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS) k_ks_mac(const u64 *__restrict__ T1, KsRoute rt, u64 *ACC, int L, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *__restrict__ T1, KsRoute rt, u64 *ACC, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int jj = blockIdx.y, b = blockIdx.z;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ks_mac(const u64 *__restrict__ 
 #pragma unroll
             for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
             __syncthreads();  // previous iteration's shared-memory reads are done
-            fwd_row_pass<LOGN>(x, tw, m.p, m.p2, t0, smem);
+            fwd_row_pass<LOGN>(x, tw, m, t0, smem);
         }
         const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
         const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_col(DView R, u64 *T2, in
     u64 x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = submod(reduce64(in[col_coarse_idx<LOGN>(c0, e)], m), hm, m.p);
-    fwd_col_pass<LOGN>(x, t.twf + (size_t)j * G::N, m.p, m.p2, smem);
+    fwd_col_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, smem);
 #pragma unroll
     for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
 }
@@ -292,13 +292,13 @@ __global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_row(const u64 *__restric
     u64 x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
-    fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m.p, m.p2, t0, smem);
+    fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, t0, smem);
     const u64 *mi = minuend.data + b * minuend.bs + s * minuend.ps + (u64)j * G::N;
     u64 *out = dst.data + sl.entry * dst.bs + s * dst.ps + (u64)j * G::N;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const int g = t0 + row_contig_li(e);
-        u64 v = csub(csub(x[e], m.p2), m.p);
+        u64 v = reduce64(x[e], m);
         u64 r = shoup_mul(submod(mi[g], v, m.p), qi, qis, m.p);
         if (MODE == 1) {
             r = addmod(r, base.data[sl.entry * base.bs + s * base.ps + (u64)j * G::N + g], m.p);

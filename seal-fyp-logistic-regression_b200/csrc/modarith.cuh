@@ -9,7 +9,7 @@
 typedef unsigned long long u64;
 
 struct ModConst {
-    u64 p;      // prime
+    u64 p;      // prime (at most 60 bits, as SEAL requires of user primes)
     u64 p2;     // 2p
     u64 r0;     // floor(2^128 / p), low word
     u64 r1;     // floor(2^128 / p), high word  (== floor(2^64 / p))
@@ -17,15 +17,43 @@ struct ModConst {
     u64 ninvs;  // Shoup companion of ninv
     u64 w1ni;   // (inverse twiddle of the root node) * N^-1 mod p
     u64 w1nis;  // its Shoup companion
+    u64 gsc;    // smallest multiple of p that is >= 4p + 2^47 (offset of the lazy inverse butterfly)
+    u64 p4;     // 4p
+    u64 negp;   // 2^64 - p (kept opaque so that w*x + q*negp stays one multiply-add chain)
+    u64 p4hi;   // high 32 bits of 4p (threshold of the cheap lazy correction)
 };
 
-// w*x mod p, lazily reduced to [0,2p); ws = floor(w * 2^64 / p), any 64-bit x, w < p
-__device__ __forceinline__ u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 p) {
+// truncated high product: floor(a*b / 2^64) - e with e in {0,1,2}.  Three multiplies instead of
+// four and no carry chain; the Shoup remainder absorbs the error (range [0,4p) instead of [0,2p)).
+__device__ __forceinline__ u64 mulhi_trunc(u64 a, u64 b) {
+    const unsigned a0 = (unsigned)a, a1 = (unsigned)(a >> 32), b0 = (unsigned)b, b1 = (unsigned)(b >> 32);
+    u64 r = (u64)a1 * b1;
+    r += (u64)__umulhi(a1, b0) + (u64)__umulhi(a0, b1);
+    return r;
+}
+
+// w*x mod p, lazily reduced to [0,4p); ws = floor(w * 2^64 / p), any 64-bit x, w < p
+__device__ __forceinline__ u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 negp) {
+    u64 q = mulhi_trunc(ws, x);
+    return w * x + q * negp;
+}
+// exact variant, [0,2p)
+__device__ __forceinline__ u64 shoup_lazy2(u64 x, u64 w, u64 ws, u64 p) {
     u64 q = __umul64hi(ws, x);
     return w * x - q * p;
 }
+// lazy correction with one 32-bit compare and a predicated subtract: removes 4p only when the high
+// word proves x > 4p.   [0, 8p + 2^32) -> [0, 4p + 2^32); exactness is restored by the final
+// Barrett reduction of each transform.
+__device__ __forceinline__ u64 lazy_sub(u64 x, u64 p4, unsigned p4hi) {
+    unsigned lo = (unsigned)x, hi = (unsigned)(x >> 32);
+    asm("{\n\t.reg .pred q;\n\tsetp.gt.u32 q, %1, %2;\n\t@q sub.cc.u32 %0, %0, %3;\n\t@q subc.u32 %1, %1, %4;\n\t}"
+        : "+r"(lo), "+r"(hi)
+        : "r"(p4hi), "r"((unsigned)p4), "r"((unsigned)(p4 >> 32)));
+    return ((u64)hi << 32) | lo;
+}
 __device__ __forceinline__ u64 csub(u64 x, u64 p) { return x >= p ? x - p : x; }
-__device__ __forceinline__ u64 shoup_mul(u64 x, u64 w, u64 ws, u64 p) { return csub(shoup_lazy(x, w, ws, p), p); }
+__device__ __forceinline__ u64 shoup_mul(u64 x, u64 w, u64 ws, u64 p) { return csub(shoup_lazy2(x, w, ws, p), p); }
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 p) { return csub(a + b, p); }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 p) { return a >= b ? a - b : a + p - b; }
 
@@ -60,18 +88,19 @@ __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
     hi += ph + (lo < pl);
 }
 
-// Harvey butterflies --------------------------------------------------------------------------
-// forward (Cooley-Tukey): X,Y in [0,4p) -> [0,4p)
-__device__ __forceinline__ void ct_bfly(u64 &X, u64 &Y, u64 w, u64 ws, u64 p, u64 p2) {
-    u64 x = X >= p2 ? X - p2 : X;
-    u64 t = shoup_lazy(Y, w, ws, p);
+// Harvey-style butterflies with relaxed ranges -----------------------------------------------------
+// forward (Cooley-Tukey): X,Y in [0, 8p + 2^32) -> [0, 8p + 2^32)
+__device__ __forceinline__ void ct_bfly(u64 &X, u64 &Y, u64 w, u64 ws, const ModConst &m) {
+    u64 x = lazy_sub(X, m.p4, (unsigned)m.p4hi);   // < 4p + 2^32
+    u64 t = shoup_lazy(Y, w, ws, m.negp);          // < 4p
     X = x + t;
-    Y = x + p2 - t;
+    Y = x + m.p4 - t;
 }
-// inverse (Gentleman-Sande): X,Y in [0,2p) -> [0,2p)
-__device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, u64 w, u64 ws, u64 p, u64 p2) {
+// inverse (Gentleman-Sande): after s stages X < 4p + 2^(31+s), Y < 4p; gsc (a multiple of p, at
+// least 4p + 2^47) keeps the difference non-negative
+__device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, u64 w, u64 ws, const ModConst &m) {
     u64 s = X + Y;
-    u64 d = X + p2 - Y;
-    X = s >= p2 ? s - p2 : s;
-    Y = shoup_lazy(d, w, ws, p);
+    u64 d = X + m.gsc - Y;
+    X = lazy_sub(s, m.p4, (unsigned)m.p4hi);
+    Y = shoup_lazy(d, w, ws, m.negp);
 }

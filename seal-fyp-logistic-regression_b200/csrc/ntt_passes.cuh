@@ -43,44 +43,44 @@ __device__ __forceinline__ int sw(int li) { return li ^ ((li >> 3) & 15); }
 // ---- radix-8 register steps ------------------------------------------------------------------
 // element e of x sits at global index base + e*stride; SKIP leading (coarse) stages are omitted
 template <int SKIP>
-__device__ __forceinline__ void fwd8(u64 (&x)[8], const tw_t *__restrict__ tw, unsigned nd, u64 p, u64 p2) {
+__device__ __forceinline__ void fwd8(u64 (&x)[8], const tw_t *__restrict__ tw, unsigned nd, const ModConst &m) {
     if (SKIP < 1) {
         tw_t w = __ldg(tw + nd);
 #pragma unroll
-        for (int e = 0; e < 4; e++) ct_bfly(x[e], x[e + 4], w.x, w.y, p, p2);
+        for (int e = 0; e < 4; e++) ct_bfly(x[e], x[e + 4], w.x, w.y, m);
     }
     if (SKIP < 2) {
         tw_t w0 = __ldg(tw + 2 * nd), w1 = __ldg(tw + 2 * nd + 1);
-        ct_bfly(x[0], x[2], w0.x, w0.y, p, p2);
-        ct_bfly(x[1], x[3], w0.x, w0.y, p, p2);
-        ct_bfly(x[4], x[6], w1.x, w1.y, p, p2);
-        ct_bfly(x[5], x[7], w1.x, w1.y, p, p2);
+        ct_bfly(x[0], x[2], w0.x, w0.y, m);
+        ct_bfly(x[1], x[3], w0.x, w0.y, m);
+        ct_bfly(x[4], x[6], w1.x, w1.y, m);
+        ct_bfly(x[5], x[7], w1.x, w1.y, m);
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         tw_t w = __ldg(tw + 4 * nd + q);
-        ct_bfly(x[2 * q], x[2 * q + 1], w.x, w.y, p, p2);
+        ct_bfly(x[2 * q], x[2 * q + 1], w.x, w.y, m);
     }
 }
 
 template <int SKIP>
-__device__ __forceinline__ void inv8(u64 (&x)[8], const tw_t *__restrict__ tw, unsigned nd, u64 p, u64 p2) {
+__device__ __forceinline__ void inv8(u64 (&x)[8], const tw_t *__restrict__ tw, unsigned nd, const ModConst &m) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         tw_t w = __ldg(tw + 4 * nd + q);
-        gs_bfly(x[2 * q], x[2 * q + 1], w.x, w.y, p, p2);
+        gs_bfly(x[2 * q], x[2 * q + 1], w.x, w.y, m);
     }
     if (SKIP < 2) {
         tw_t w0 = __ldg(tw + 2 * nd), w1 = __ldg(tw + 2 * nd + 1);
-        gs_bfly(x[0], x[2], w0.x, w0.y, p, p2);
-        gs_bfly(x[1], x[3], w0.x, w0.y, p, p2);
-        gs_bfly(x[4], x[6], w1.x, w1.y, p, p2);
-        gs_bfly(x[5], x[7], w1.x, w1.y, p, p2);
+        gs_bfly(x[0], x[2], w0.x, w0.y, m);
+        gs_bfly(x[1], x[3], w0.x, w0.y, m);
+        gs_bfly(x[4], x[6], w1.x, w1.y, m);
+        gs_bfly(x[5], x[7], w1.x, w1.y, m);
     }
     if (SKIP < 1) {
         tw_t w = __ldg(tw + nd);
 #pragma unroll
-        for (int e = 0; e < 4; e++) gs_bfly(x[e], x[e + 4], w.x, w.y, p, p2);
+        for (int e = 0; e < 4; e++) gs_bfly(x[e], x[e + 4], w.x, w.y, m);
     }
 }
 
@@ -99,39 +99,38 @@ __device__ __forceinline__ int col_fine_idx(int c0, int e) {
     return (8 * k + e) * NttGeo<LOGN>::N2 + c0 + lane;
 }
 
-// forward: x holds the coarse-side elements (values < 4p); returns fine-side elements in [0,4p)
+// forward: x holds the coarse-side elements (values < 8p); returns fine-side elements, lazy (< 8p + 2^32)
 template <int LOGN>
-__device__ __forceinline__ void fwd_col_pass(u64 (&x)[8], const tw_t *__restrict__ tw, u64 p, u64 p2, u64 *smem) {
+__device__ __forceinline__ void fwd_col_pass(u64 (&x)[8], const tw_t *__restrict__ tw, const ModConst &m, u64 *smem) {
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    fwd8<0>(x, tw, 1u, p, p2);  // stages 0..2, root node
+    fwd8<0>(x, tw, 1u, m);  // stages 0..2, root node
 #pragma unroll
     for (int e = 0; e < 8; e++) smem[(k + 8 * e) * 32 + lane] = x[e];
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = smem[(8 * k + e) * 32 + lane];
-    fwd8<0>(x, tw, 8u + k, p, p2);  // stages 3..5
+    fwd8<0>(x, tw, 8u + k, m);  // stages 3..5
 }
 
 // inverse: x holds fine-side elements in [0,2p); returns coarse-side elements, scaled by N^-1,
-// in [0,2p)
+// in [0,4p)
 template <int LOGN>
 __device__ __forceinline__ void inv_col_pass(u64 (&x)[8], const tw_t *__restrict__ twi, const ModConst &m, u64 *smem) {
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u64 p = m.p, p2 = m.p2;
-    inv8<0>(x, twi, 8u + k, p, p2);  // stages 5..3
+    inv8<0>(x, twi, 8u + k, m);  // stages 5..3
 #pragma unroll
     for (int e = 0; e < 8; e++) smem[(8 * k + e) * 32 + lane] = x[e];
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = smem[(k + 8 * e) * 32 + lane];
-    inv8<1>(x, twi, 1u, p, p2);  // stages 2..1
+    inv8<1>(x, twi, 1u, m);  // stages 2..1
     // stage 0 with N^-1 folded into both outputs
 #pragma unroll
     for (int e = 0; e < 4; e++) {
         u64 s = x[e] + x[e + 4];
-        u64 d = x[e] + p2 - x[e + 4];
-        x[e] = shoup_lazy(s, m.ninv, m.ninvs, p);
-        x[e + 4] = shoup_lazy(d, m.w1ni, m.w1nis, p);
+        u64 d = x[e] + m.gsc - x[e + 4];
+        x[e] = shoup_lazy(s, m.ninv, m.ninvs, m.negp);
+        x[e + 4] = shoup_lazy(d, m.w1ni, m.w1nis, m.negp);
     }
 }
 
@@ -156,49 +155,48 @@ __device__ __forceinline__ int row_mid_li(int e) {
     return rr * G::N2 + a * G::T + k2 + T8 * e;
 }
 
-// forward: x = strided-side elements (< 4p) -> contiguous-side elements in [0,4p)
+// forward: x = strided-side elements (lazy) -> contiguous-side elements, lazy (< 8p + 2^32)
 template <int LOGN>
-__device__ __forceinline__ void fwd_row_pass(u64 (&x)[8], const tw_t *__restrict__ tw, u64 p, u64 p2, int t0, u64 *smem) {
+__device__ __forceinline__ void fwd_row_pass(u64 (&x)[8], const tw_t *__restrict__ tw, const ModConst &m, int t0, u64 *smem) {
     typedef NttGeo<LOGN> G;
     // stages 6..8
-    fwd8<0>(x, tw, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)), p, p2);
+    fwd8<0>(x, tw, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)), m);
 #pragma unroll
     for (int e = 0; e < 8; e++) smem[sw(row_strided_li<LOGN>(e))] = x[e];
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = smem[sw(row_mid_li<LOGN>(e))];
     // stages 9..11
-    fwd8<0>(x, tw, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)), p, p2);
+    fwd8<0>(x, tw, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)), m);
     if (G::REM > 0) {
-        __syncthreads();
+        // each thread overwrites exactly the slots it has just read: no barrier needed before
 #pragma unroll
         for (int e = 0; e < 8; e++) smem[sw(row_mid_li<LOGN>(e))] = x[e];
         __syncthreads();
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = smem[sw(row_contig_li(e))];
         // last REM stages; virtual root stage is n-3
-        fwd8<3 - (G::REM > 0 ? G::REM : 3)>(x, tw, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3), p, p2);
+        fwd8<3 - (G::REM > 0 ? G::REM : 3)>(x, tw, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3), m);
     }
 }
 
-// inverse: x = contiguous-side elements in [0,2p) -> strided-side elements in [0,2p)
+// inverse: x = contiguous-side elements in [0,2p) -> strided-side elements, lazy (< 4p + 2^47)
 template <int LOGN>
-__device__ __forceinline__ void inv_row_pass(u64 (&x)[8], const tw_t *__restrict__ twi, u64 p, u64 p2, int t0, u64 *smem) {
+__device__ __forceinline__ void inv_row_pass(u64 (&x)[8], const tw_t *__restrict__ twi, const ModConst &m, int t0, u64 *smem) {
     typedef NttGeo<LOGN> G;
     if (G::REM > 0) {
-        inv8<3 - (G::REM > 0 ? G::REM : 3)>(x, twi, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3), p, p2);
+        inv8<3 - (G::REM > 0 ? G::REM : 3)>(x, twi, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3), m);
 #pragma unroll
         for (int e = 0; e < 8; e++) smem[sw(row_contig_li(e))] = x[e];
         __syncthreads();
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = smem[sw(row_mid_li<LOGN>(e))];
     }
-    inv8<0>(x, twi, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)), p, p2);
-    if (G::REM > 0) __syncthreads();
+    inv8<0>(x, twi, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)), m);
 #pragma unroll
-    for (int e = 0; e < 8; e++) smem[sw(row_mid_li<LOGN>(e))] = x[e];
+    for (int e = 0; e < 8; e++) smem[sw(row_mid_li<LOGN>(e))] = x[e];   // same slots this thread read
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = smem[sw(row_strided_li<LOGN>(e))];
-    inv8<0>(x, twi, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)), p, p2);
+    inv8<0>(x, twi, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)), m);
 }

@@ -78,7 +78,7 @@ static uint64_t smallest_primitive_root(uint64_t p, uint64_t order) {
 void build_tables(int log_n, const std::vector<uint64_t> &primes, HostTables &out) {
     const size_t n = size_t(1) << log_n;
     const size_t K = primes.size();
-    out.mod.assign(K * 8, 0);
+    out.mod.assign(K * 12, 0);
     out.twf.assign(K * n * 2, 0);
     out.twi.assign(K * n * 2, 0);
     out.inv.assign(K * K, 0);
@@ -86,8 +86,8 @@ void build_tables(int log_n, const std::vector<uint64_t> &primes, HostTables &ou
     out.halfmod.assign(K * K, 0);
     for (size_t j = 0; j < K; ++j) {
         const uint64_t p = primes[j];
-        if ((p >> 61) != 0 || !is_prime_u64(p) || (p - 1) % (2 * n) != 0)
-            throw std::invalid_argument("coeff_modulus primes must be < 2^61, prime and 1 mod 2N");
+        if ((p >> 60) != 0 || !is_prime_u64(p) || (p - 1) % (2 * n) != 0)
+            throw std::invalid_argument("coeff_modulus primes must be at most 60 bits, prime and 1 mod 2N");
         for (size_t i = 0; i < j; ++i)
             if (primes[i] == p) throw std::invalid_argument("coeff_modulus primes must be distinct");
         const u128 ratio = (~(u128)0) / p;
@@ -105,7 +105,7 @@ void build_tables(int log_n, const std::vector<uint64_t> &primes, HostTables &ou
             ti[2 * node] = inv_mod(tf[2 * node], p);
             ti[2 * node + 1] = shoup_of(ti[2 * node], p);
         }
-        uint64_t *m = &out.mod[j * 8];
+        uint64_t *m = &out.mod[j * 12];
         m[0] = p;
         m[1] = 2 * p;
         m[2] = (uint64_t)ratio;
@@ -114,6 +114,11 @@ void build_tables(int log_n, const std::vector<uint64_t> &primes, HostTables &ou
         m[5] = shoup_of(n_inv, p);
         m[6] = mul_mod(ti[2 * 1], n_inv, p);  // root node of the inverse tree times N^-1
         m[7] = shoup_of(m[6], p);
+        const uint64_t need = 4 * p + (uint64_t(1) << 47);
+        m[8] = ((need + p - 1) / p) * p;   // multiple of p covering every lazy inverse-butterfly operand
+        m[9] = 4 * p;
+        m[10] = 0 - p;
+        m[11] = (4 * p) >> 32;
     }
     for (size_t a = 0; a < K; ++a)
         for (size_t j = 0; j < K; ++j) {

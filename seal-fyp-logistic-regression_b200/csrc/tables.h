@@ -6,7 +6,7 @@
 namespace ckks {
 
 struct HostTables {
-    std::vector<uint64_t> mod;      // [K][8]  {p, 2p, ratio_lo, ratio_hi, N^-1, shoup, w1*N^-1, shoup}
+    std::vector<uint64_t> mod;      // [K][12] {p, 2p, ratio_lo, ratio_hi, N^-1, shoup, w1*N^-1, shoup, gsc, 4p, 2^64-p, hi32(4p)}
     std::vector<uint64_t> twf;      // [K][N][2] forward twiddle tree {w, shoup(w)}
     std::vector<uint64_t> twi;      // [K][N][2] inverse twiddle tree
     std::vector<uint64_t> inv;      // [K][K]  q_a^-1 mod q_j
