@@ -32,6 +32,30 @@ struct DView {
 
 __device__ __forceinline__ ModConst load_mod(const Tables &t, int j) { return t.mod[j]; }
 
+// eight contiguous words of a thread (64 bytes) as four 16-byte accesses
+__device__ __forceinline__ void load8(u64 (&x)[8], const u64 *p) {
+    const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(p);
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        ulonglong2 a = q[v];
+        x[2 * v] = a.x;
+        x[2 * v + 1] = a.y;
+    }
+}
+__device__ __forceinline__ void store8(u64 *p, const u64 (&x)[8]) {
+    ulonglong2 *q = reinterpret_cast<ulonglong2 *>(p);
+#pragma unroll
+    for (int v = 0; v < 4; v++) q[v] = make_ulonglong2(x[2 * v], x[2 * v + 1]);
+}
+// the thread's eight source indices of a Galois gather (32 contiguous bytes of the table)
+__device__ __forceinline__ void load_perm8(unsigned (&ix)[8], const uint32_t *perm) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(perm);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    ix[0] = a.x; ix[1] = a.y; ix[2] = a.z; ix[3] = a.w;
+    ix[4] = b.x; ix[5] = b.y; ix[6] = b.z; ix[7] = b.w;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Per-entry routing of a batched key switch: which ciphertext of the views a launch slot works
 // on, which key/permutation it uses, and which of the three views (0 = in, 1 = out, 2 = scratch)
 // it reads from and writes to.  With sel == nullptr slot z works on entry z with key 0,
@@ -98,7 +122,8 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_row(DView src, DView dst, i
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
     fwd_row_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, t0, smem);
 #pragma unroll
-    for (int e = 0; e < 8; e++) out[t0 + row_contig_li(e)] = reduce64(x[e], m);
+    for (int e = 0; e < 8; e++) x[e] = reduce64(x[e], m);
+    store8(out + t0 + 8 * threadIdx.x, x);
 }
 
 template <int LOGN>
@@ -111,8 +136,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_inv_row(DView src, DView dst, i
     const ModConst m = load_mod(t, pj);
     const int t0 = blockIdx.x * NTT_TILE;
     u64 x[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) x[e] = in[t0 + row_contig_li(e)];
+    load8(x, in + t0 + 8 * threadIdx.x);
     inv_row_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m, t0, smem);
 #pragma unroll
     for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = x[e];  // lazy
@@ -160,10 +184,13 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ks_intt_row(KsRoute rt, u64 *D,
     const ModConst m = load_mod(t, i);
     const int t0 = blockIdx.x * NTT_TILE;
     u64 x[8];
+    if (GALOIS) {
+        unsigned ix[8];
+        load_perm8(ix, perm + t0 + 8 * threadIdx.x);
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        int g = t0 + row_contig_li(e);
-        x[e] = in[GALOIS ? perm[g] : g];
+        for (int e = 0; e < 8; e++) x[e] = in[ix[e]];
+    } else {
+        load8(x, in + t0 + 8 * threadIdx.x);
     }
     inv_row_pass<LOGN>(x, t.twi + (size_t)i * G::N, m, t0, smem);
 #pragma unroll
@@ -212,12 +239,18 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *__restrict
     for (int e = 0; e < 8; e++) lo0[e] = hi0[e] = lo1[e] = hi1[e] = 0;
     for (int i = 0; i < L; i++) {
         u64 x[8];
+        // the key stream comes from HBM: start it before the transform of this digit
+        prefetch_l2(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+        prefetch_l2(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
         if (i == pj) {
             const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
+            if (GALOIS) {
+                unsigned ix[8];
+                load_perm8(ix, perm + t0 + 8 * threadIdx.x);
 #pragma unroll
-            for (int e = 0; e < 8; e++) {
-                int g = t0 + row_contig_li(e);
-                x[e] = in[GALOIS ? perm[g] : g];
+                for (int e = 0; e < 8; e++) x[e] = in[ix[e]];
+            } else {
+                load8(x, in + t0 + 8 * threadIdx.x);
             }
         } else {
             const u64 *in = T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N;
@@ -293,20 +326,31 @@ __global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_row(const u64 *__restric
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
     fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, t0, smem);
-    const u64 *mi = minuend.data + b * minuend.bs + s * minuend.ps + (u64)j * G::N;
-    u64 *out = dst.data + sl.entry * dst.bs + s * dst.ps + (u64)j * G::N;
+    const u64 *mi = minuend.data + b * minuend.bs + s * minuend.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
+    u64 *out = dst.data + sl.entry * dst.bs + s * dst.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
+    // all epilogue loads are issued before the first store (out may alias base, so the compiler
+    // would otherwise serialise load -> store -> load ...)
+    u64 mv[8], bv[8];
+    load8(mv, mi);
+    if (MODE == 1) {
+        load8(bv, base.data + sl.entry * base.bs + s * base.ps + (u64)j * G::N + t0 + 8 * threadIdx.x);
+    } else if (MODE == 2) {
+        if (s == 0) {
+            unsigned ix[8];
+            load_perm8(ix, perm + t0 + 8 * threadIdx.x);
+            const u64 *bp = base.data + sl.entry * base.bs + (u64)j * G::N;
+#pragma unroll
+            for (int e = 0; e < 8; e++) bv[e] = bp[ix[e]];
+        }
+    }
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-        const int g = t0 + row_contig_li(e);
         u64 v = reduce64(x[e], m);
-        u64 r = shoup_mul(submod(mi[g], v, m.p), qi, qis, m.p);
-        if (MODE == 1) {
-            r = addmod(r, base.data[sl.entry * base.bs + s * base.ps + (u64)j * G::N + g], m.p);
-        } else if (MODE == 2) {
-            if (s == 0) r = addmod(r, base.data[sl.entry * base.bs + (u64)j * G::N + perm[g]], m.p);
-        }
-        out[g] = r;
+        u64 r = shoup_mul(submod(mv[e], v, m.p), qi, qis, m.p);
+        if (MODE == 1 || (MODE == 2 && s == 0)) r = addmod(r, bv[e], m.p);
+        x[e] = r;
     }
+    store8(out, x);
 }
 
 // =============================================================================== element-wise
