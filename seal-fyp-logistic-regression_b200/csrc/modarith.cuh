@@ -81,11 +81,27 @@ __device__ __forceinline__ u64 mulmod(u64 a, u64 b, const ModConst &m) {
     return barrett128(a * b, __umul64hi(a, b), m);
 }
 
-// 128-bit accumulate: (lo,hi) += a*b
+// 128-bit accumulate: (lo,hi) += a*b.  The four 32x32 partial products are added straight into
+// the accumulator words with one carry chain (4 wide multiplies, no separate lo/hi products).
 __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
-    u64 pl = a * b, ph = __umul64hi(a, b);
-    lo += pl;
-    hi += ph + (lo < pl);
+    unsigned a0 = (unsigned)a, a1 = (unsigned)(a >> 32), b0 = (unsigned)b, b1 = (unsigned)(b >> 32);
+    unsigned r0 = (unsigned)lo, r1 = (unsigned)(lo >> 32), r2 = (unsigned)hi, r3 = (unsigned)(hi >> 32);
+    asm("{\n\t"
+        "mad.lo.cc.u32   %0, %4, %6, %0;\n\t"     // a0*b0 lo -> r0
+        "madc.hi.cc.u32  %1, %4, %6, %1;\n\t"     // a0*b0 hi -> r1
+        "madc.lo.cc.u32  %2, %5, %7, %2;\n\t"     // a1*b1 lo -> r2
+        "madc.hi.u32     %3, %5, %7, %3;\n\t"     // a1*b1 hi -> r3
+        "mad.lo.cc.u32   %1, %4, %7, %1;\n\t"     // a0*b1 lo -> r1
+        "madc.hi.cc.u32  %2, %4, %7, %2;\n\t"     // a0*b1 hi -> r2
+        "addc.u32        %3, %3, 0;\n\t"
+        "mad.lo.cc.u32   %1, %5, %6, %1;\n\t"     // a1*b0 lo -> r1
+        "madc.hi.cc.u32  %2, %5, %6, %2;\n\t"     // a1*b0 hi -> r2
+        "addc.u32        %3, %3, 0;\n\t"
+        "}"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    lo = ((u64)r1 << 32) | r0;
+    hi = ((u64)r3 << 32) | r2;
 }
 
 // Harvey-style butterflies with relaxed ranges -----------------------------------------------------
