@@ -41,47 +41,64 @@ typedef ulonglong2 tw_t;  // {w, floor(w 2^64 / p)}
 __device__ __forceinline__ int sw(int li) { return li ^ ((li >> 3) & 15); }
 
 // ---- radix-8 register steps ------------------------------------------------------------------
-// element e of x sits at global index base + e*stride; SKIP leading (coarse) stages are omitted
+// element e of x sits at global index base + e*stride; SKIP leading (coarse) stages are omitted.
+// Twiddle loading is split from the arithmetic so that callers can issue the loads of the next
+// step before a shared-memory exchange and have them in flight across the barrier.
+struct Tw8 {
+    tw_t w[7];   // node nd | 2nd, 2nd+1 | 4nd .. 4nd+3
+};
 template <int SKIP>
-__device__ __forceinline__ void fwd8(u64 (&x)[8], const tw_t *__restrict__ tw, unsigned nd, const ModConst &m) {
-    if (SKIP < 1) {
-        tw_t w = __ldg(tw + nd);
+__device__ __forceinline__ void load_tw8(Tw8 &t, const tw_t *__restrict__ tw, unsigned nd) {
+    if (SKIP < 1) t.w[0] = __ldg(tw + nd);
+    if (SKIP < 2) {
+        t.w[1] = __ldg(tw + 2 * nd);
+        t.w[2] = __ldg(tw + 2 * nd + 1);
+    }
 #pragma unroll
-        for (int e = 0; e < 4; e++) ct_bfly(x[e], x[e + 4], w.x, w.y, m);
+    for (int q = 0; q < 4; q++) t.w[3 + q] = __ldg(tw + 4 * nd + q);
+}
+template <int SKIP>
+__device__ __forceinline__ void fwd8(u64 (&x)[8], const Tw8 &t, const ModConst &m) {
+    if (SKIP < 1) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) ct_bfly(x[e], x[e + 4], t.w[0].x, t.w[0].y, m);
     }
     if (SKIP < 2) {
-        tw_t w0 = __ldg(tw + 2 * nd), w1 = __ldg(tw + 2 * nd + 1);
-        ct_bfly(x[0], x[2], w0.x, w0.y, m);
-        ct_bfly(x[1], x[3], w0.x, w0.y, m);
-        ct_bfly(x[4], x[6], w1.x, w1.y, m);
-        ct_bfly(x[5], x[7], w1.x, w1.y, m);
+        ct_bfly(x[0], x[2], t.w[1].x, t.w[1].y, m);
+        ct_bfly(x[1], x[3], t.w[1].x, t.w[1].y, m);
+        ct_bfly(x[4], x[6], t.w[2].x, t.w[2].y, m);
+        ct_bfly(x[5], x[7], t.w[2].x, t.w[2].y, m);
     }
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        tw_t w = __ldg(tw + 4 * nd + q);
-        ct_bfly(x[2 * q], x[2 * q + 1], w.x, w.y, m);
+    for (int q = 0; q < 4; q++) ct_bfly(x[2 * q], x[2 * q + 1], t.w[3 + q].x, t.w[3 + q].y, m);
+}
+template <int SKIP>
+__device__ __forceinline__ void inv8(u64 (&x)[8], const Tw8 &t, const ModConst &m) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) gs_bfly(x[2 * q], x[2 * q + 1], t.w[3 + q].x, t.w[3 + q].y, m);
+    if (SKIP < 2) {
+        gs_bfly(x[0], x[2], t.w[1].x, t.w[1].y, m);
+        gs_bfly(x[1], x[3], t.w[1].x, t.w[1].y, m);
+        gs_bfly(x[4], x[6], t.w[2].x, t.w[2].y, m);
+        gs_bfly(x[5], x[7], t.w[2].x, t.w[2].y, m);
+    }
+    if (SKIP < 1) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) gs_bfly(x[e], x[e + 4], t.w[0].x, t.w[0].y, m);
     }
 }
-
+// convenience: load + apply
+template <int SKIP>
+__device__ __forceinline__ void fwd8(u64 (&x)[8], const tw_t *__restrict__ tw, unsigned nd, const ModConst &m) {
+    Tw8 t;
+    load_tw8<SKIP>(t, tw, nd);
+    fwd8<SKIP>(x, t, m);
+}
 template <int SKIP>
 __device__ __forceinline__ void inv8(u64 (&x)[8], const tw_t *__restrict__ tw, unsigned nd, const ModConst &m) {
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        tw_t w = __ldg(tw + 4 * nd + q);
-        gs_bfly(x[2 * q], x[2 * q + 1], w.x, w.y, m);
-    }
-    if (SKIP < 2) {
-        tw_t w0 = __ldg(tw + 2 * nd), w1 = __ldg(tw + 2 * nd + 1);
-        gs_bfly(x[0], x[2], w0.x, w0.y, m);
-        gs_bfly(x[1], x[3], w0.x, w0.y, m);
-        gs_bfly(x[4], x[6], w1.x, w1.y, m);
-        gs_bfly(x[5], x[7], w1.x, w1.y, m);
-    }
-    if (SKIP < 1) {
-        tw_t w = __ldg(tw + nd);
-#pragma unroll
-        for (int e = 0; e < 4; e++) gs_bfly(x[e], x[e + 4], w.x, w.y, m);
-    }
+    Tw8 t;
+    load_tw8<SKIP>(t, tw, nd);
+    inv8<SKIP>(x, t, m);
 }
 
 // ---- column pass -------------------------------------------------------------------------------
@@ -104,12 +121,14 @@ template <int LOGN>
 __device__ __forceinline__ void fwd_col_pass(u64 (&x)[8], const tw_t *__restrict__ tw, const ModConst &m, u64 *smem) {
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     fwd8<0>(x, tw, 1u, m);  // stages 0..2, root node
+    Tw8 t2;
+    load_tw8<0>(t2, tw, 8u + k);   // in flight across the exchange
 #pragma unroll
     for (int e = 0; e < 8; e++) smem[(k + 8 * e) * 32 + lane] = x[e];
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = smem[(8 * k + e) * 32 + lane];
-    fwd8<0>(x, tw, 8u + k, m);  // stages 3..5
+    fwd8<0>(x, t2, m);  // stages 3..5
 }
 
 // inverse: x holds fine-side elements in [0,2p); returns coarse-side elements, scaled by N^-1,
@@ -118,12 +137,14 @@ template <int LOGN>
 __device__ __forceinline__ void inv_col_pass(u64 (&x)[8], const tw_t *__restrict__ twi, const ModConst &m, u64 *smem) {
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     inv8<0>(x, twi, 8u + k, m);  // stages 5..3
+    Tw8 t2;
+    load_tw8<1>(t2, twi, 1u);
 #pragma unroll
     for (int e = 0; e < 8; e++) smem[(8 * k + e) * 32 + lane] = x[e];
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = smem[(k + 8 * e) * 32 + lane];
-    inv8<1>(x, twi, 1u, m);  // stages 2..1
+    inv8<1>(x, t2, m);  // stages 2..1
     // stage 0 with N^-1 folded into both outputs
 #pragma unroll
     for (int e = 0; e < 4; e++) {
@@ -159,16 +180,21 @@ __device__ __forceinline__ int row_mid_li(int e) {
 template <int LOGN>
 __device__ __forceinline__ void fwd_row_pass(u64 (&x)[8], const tw_t *__restrict__ tw, const ModConst &m, int t0, u64 *smem) {
     typedef NttGeo<LOGN> G;
+    constexpr int SK3 = 3 - (G::REM > 0 ? G::REM : 3);
+    Tw8 ta, tb;
     // stages 6..8
-    fwd8<0>(x, tw, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)), m);
+    load_tw8<0>(ta, tw, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)));
+    fwd8<0>(x, ta, m);
+    load_tw8<0>(tb, tw, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)));   // next step, in flight
 #pragma unroll
     for (int e = 0; e < 8; e++) smem[sw(row_strided_li<LOGN>(e))] = x[e];
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = smem[sw(row_mid_li<LOGN>(e))];
     // stages 9..11
-    fwd8<0>(x, tw, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)), m);
+    fwd8<0>(x, tb, m);
     if (G::REM > 0) {
+        load_tw8<SK3>(ta, tw, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3));
         // each thread overwrites exactly the slots it has just read: no barrier needed before
 #pragma unroll
         for (int e = 0; e < 8; e++) smem[sw(row_mid_li<LOGN>(e))] = x[e];
@@ -176,7 +202,7 @@ __device__ __forceinline__ void fwd_row_pass(u64 (&x)[8], const tw_t *__restrict
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = smem[sw(row_contig_li(e))];
         // last REM stages; virtual root stage is n-3
-        fwd8<3 - (G::REM > 0 ? G::REM : 3)>(x, tw, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3), m);
+        fwd8<SK3>(x, ta, m);
     }
 }
 
@@ -184,19 +210,24 @@ __device__ __forceinline__ void fwd_row_pass(u64 (&x)[8], const tw_t *__restrict
 template <int LOGN>
 __device__ __forceinline__ void inv_row_pass(u64 (&x)[8], const tw_t *__restrict__ twi, const ModConst &m, int t0, u64 *smem) {
     typedef NttGeo<LOGN> G;
+    constexpr int SK3 = 3 - (G::REM > 0 ? G::REM : 3);
+    Tw8 ta, tb;
+    load_tw8<0>(tb, twi, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)));
     if (G::REM > 0) {
-        inv8<3 - (G::REM > 0 ? G::REM : 3)>(x, twi, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3), m);
+        load_tw8<SK3>(ta, twi, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3));
+        inv8<SK3>(x, ta, m);
 #pragma unroll
         for (int e = 0; e < 8; e++) smem[sw(row_contig_li(e))] = x[e];
         __syncthreads();
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = smem[sw(row_mid_li<LOGN>(e))];
     }
-    inv8<0>(x, twi, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)), m);
+    inv8<0>(x, tb, m);
+    load_tw8<0>(ta, twi, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)));
 #pragma unroll
     for (int e = 0; e < 8; e++) smem[sw(row_mid_li<LOGN>(e))] = x[e];   // same slots this thread read
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = smem[sw(row_strided_li<LOGN>(e))];
-    inv8<0>(x, twi, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)), m);
+    inv8<0>(x, ta, m);
 }
