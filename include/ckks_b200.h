@@ -157,6 +157,15 @@ int ckks_rotplan_rounds(const ckks_rotplan *plan);
 int ckks_rotate_plan(ckks_ctx *ctx, const ckks_rotplan *plan, const ckks_view *in, const ckks_view *out,
                      const ckks_view *scratch, ckks_stream s);
 
+/* The rotate-and-sum loop of cipher_dot_product (helper.h:472-476), `count` times:
+ *     dup = rotate_vector(dup, steps);  acc = acc + dup
+ * on a batch of independent ciphertexts.  `a` holds dup on entry; the rotation ping-pongs between
+ * a and b (distinct storage, same shape), the add is fused into the key switch, and pairs of steps
+ * are replayed from a cached CUDA graph.  *final_in_b tells where dup ended up.  The key for
+ * `steps` itself must be present (the loop uses step 1). */
+int ckks_rotate_sum_chain(ckks_ctx *ctx, const ckks_keyset *ks, const ckks_view *a, const ckks_view *b,
+                          const ckks_view *acc, int steps, int count, int *final_in_b, ckks_stream s);
+
 /* ---- fused multiply + add_many (bit-identical to the sequential ops: sums are modulo q)
  * out (batch 1) = sum_b cts[b] (.) pts[b]        -- multiply_plain + add_many, helper.h:250-259 */
 int ckks_multiply_plain_sum(ckks_ctx *ctx, const ckks_view *cts, const ckks_view *pts, const ckks_view *out,

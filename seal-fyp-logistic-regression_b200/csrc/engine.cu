@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -46,6 +47,14 @@ struct ckks_ctx {
     size_t ws_bytes = 0;
     size_t ws_cap = size_t(1) << 30;
     uint64_t launches = 0;
+    // rotate-and-sum chains: private stream + cached CUDA graphs of two ping-pong steps
+    cudaStream_t chain_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    struct ChainGraph {
+        cudaGraphExec_t exec;
+        uint64_t launches;
+    };
+    std::map<std::vector<uint64_t>, ChainGraph> chain_graphs;
 };
 
 struct ckks_keyset {
@@ -129,6 +138,10 @@ extern "C" void ckks_ctx_destroy(ckks_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto &kv : c->perms) cudaFree(kv.second);
+    for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
+    if (c->chain_stream) cudaStreamDestroy(c->chain_stream);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_out) cudaEventDestroy(c->ev_out);
     cudaFree(c->d_mod); cudaFree(c->d_twf); cudaFree(c->d_twi);
     cudaFree(c->d_inv); cudaFree(c->d_invs); cudaFree(c->d_half);
     cudaFree(c->ws);
@@ -563,6 +576,91 @@ extern "C" int ckks_rotate(ckks_ctx *c, const ckks_keyset *ks, const ckks_view *
         if ((rc = ckks_apply_galois(c, cur, gt, ks->galois.at(gt), dstv, s))) return rc;
         cur = dstv;
     }
+    return CKKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ rotate-and-sum chain
+// `count` iterations of   dup = rotate_vector(dup, steps);  acc += dup   (cipher_dot_product's loop,
+// helper.h:472-476) on a batch of independent ciphertexts.  The rotation ping-pongs between the
+// views a and b (a holds dup on entry); the add is fused into the key switch's last kernel; two
+// steps (a->b, b->a) are captured once into a CUDA graph and replayed, so the dependent chain costs
+// one graph launch per two key switches instead of 18 kernel launches.
+extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const ckks_view *a, const ckks_view *b,
+                                     const ckks_view *acc, int steps, int count, int *final_in_b, ckks_stream s) {
+    int rc;
+    if (!ks) return fail(CKKS_ERR_INVALID, "null keyset");
+    if ((rc = check_view(c, a, "a")) || (rc = check_view(c, b, "b")) || (rc = check_view(c, acc, "acc"))) return rc;
+    if ((rc = same_shape(a, b, "b")) || (rc = same_shape(a, acc, "acc"))) return rc;
+    if (a->size != 2) return fail(CKKS_ERR_INVALID, "encrypted size must be 2");
+    if (a->limbs > c->K - 1) return fail(CKKS_ERR_INVALID, "encrypted is not valid for encryption parameters");
+    if (a->data == b->data || a->data == acc->data || b->data == acc->data) return fail(CKKS_ERR_INVALID, "a, b and acc must be distinct storage");
+    if (count < 0) return fail(CKKS_ERR_INVALID, "negative count");
+    uint64_t g = ckks::galois_elt_from_step(c->log_n, steps);
+    if (!g) return fail(CKKS_ERR_INVALID, "step count too large");
+    auto it = ks->galois.find(g);
+    if (it == ks->galois.end()) return fail(CKKS_ERR_INVALID, "Galois key not present");
+    const uint32_t *perm = nullptr;
+    if ((rc = get_perm(c, g, &perm))) return rc;
+    CU(cudaSetDevice(c->device));
+    const int L = a->limbs, B = a->batch;
+    if ((rc = ensure_ws(c, ks_words_per_ct(c, L) * 8 * (size_t)ks_chunk(c, B, L)))) return rc;
+    cudaStream_t user = (cudaStream_t)s;
+    auto one = [&](const ckks_view *src, const ckks_view *dst, cudaStream_t st) -> int {
+        KsRoute rt = uniform_route(src, dst, perm, it->second);
+        rt.accv = dv(acc);
+        rt.has_acc = 1;
+        return keyswitch(c, 2, L, B, rt, st);
+    };
+    int done = 0;
+    if (count >= 4) {
+        if (!c->chain_stream) {
+            CU(cudaStreamCreateWithFlags(&c->chain_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+        }
+        std::vector<uint64_t> key = {(uint64_t)a->data, (uint64_t)b->data, (uint64_t)acc->data, (uint64_t)it->second, g,
+                                     (uint64_t)L, (uint64_t)B, a->batch_stride, a->poly_stride, b->batch_stride, b->poly_stride,
+                                     acc->batch_stride, acc->poly_stride, (uint64_t)c->ws, (uint64_t)c->t.round_half};
+        auto gi = c->chain_graphs.find(key);
+        if (gi == c->chain_graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            uint64_t before = c->launches;
+            CU(cudaStreamBeginCapture(c->chain_stream, cudaStreamCaptureModeThreadLocal));
+            rc = one(a, b, c->chain_stream);
+            if (!rc) rc = one(b, a, c->chain_stream);
+            cudaError_t ce = cudaStreamEndCapture(c->chain_stream, &graph);
+            uint64_t per = c->launches - before;
+            c->launches = before;
+            if (rc) return rc;
+            if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+            ckks_ctx::ChainGraph cg{};
+            cg.launches = per;
+            ce = cudaGraphInstantiate(&cg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+            if (c->chain_graphs.size() > 64) {   // bounded cache
+                for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
+                c->chain_graphs.clear();
+            }
+            gi = c->chain_graphs.emplace(key, cg).first;
+        }
+        CU(cudaEventRecord(c->ev_in, user));
+        CU(cudaStreamWaitEvent(c->chain_stream, c->ev_in, 0));
+        const int pairs = count / 2;
+        for (int i = 0; i < pairs; i++) CU(cudaGraphLaunch(gi->second.exec, c->chain_stream));
+        c->launches += gi->second.launches * (uint64_t)pairs;
+        CU(cudaEventRecord(c->ev_out, c->chain_stream));
+        CU(cudaStreamWaitEvent(user, c->ev_out, 0));
+        done = pairs * 2;
+    }
+    const ckks_view *src = a, *dst = b;
+    for (; done < count; done++) {
+        if ((rc = one(src, dst, user))) return rc;
+        const ckks_view *t = src;
+        src = dst;
+        dst = t;
+    }
+    if (final_in_b) *final_in_b = (src == b) ? 1 : 0;
     return CKKS_OK;
 }
 

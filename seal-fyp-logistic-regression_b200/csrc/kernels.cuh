@@ -75,6 +75,8 @@ struct KsRoute {
     const u64 *key0;
     int b0;                            // first launch slot of this chunk
     int tgt_poly;                      // polynomial that is key-switched (2 relin, 1 Galois)
+    DView accv;                        // optional: accv[entry] += result (rotate-and-sum chains)
+    int has_acc;
 };
 __device__ __forceinline__ KsSel route_sel(const KsRoute &r, int z) {
     if (r.sel) return r.sel[r.b0 + z];
@@ -351,6 +353,15 @@ __global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_row(const u64 *__restric
         x[e] = r;
     }
     store8(out, x);
+    if (MODE == 2 && rt.has_acc) {
+        // add_inplace(acc, rotated) of the rotate-and-sum loop (helper.h:472-476), fused
+        u64 *ap = rt.accv.data + sl.entry * rt.accv.bs + s * rt.accv.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
+        u64 av[8];
+        load8(av, ap);
+#pragma unroll
+        for (int e = 0; e < 8; e++) av[e] = addmod(av[e], x[e], m.p);
+        store8(ap, av);
+    }
 }
 
 // =============================================================================== element-wise

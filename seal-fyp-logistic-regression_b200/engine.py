@@ -404,6 +404,21 @@ class Evaluator:
         out.scale = ct.scale
         return out
 
+    def rotate_sum_chain(self, dup, acc, steps, count, keys, scratch=None):
+        """`count` times: dup = rotate_vector(dup, steps); acc += dup (fused, CUDA-graph replayed).
+        Returns the Ciphertext that holds dup afterwards (dup's or scratch's storage)."""
+        if dup.limbs != acc.limbs or dup.batch != acc.batch:
+            raise capi.CkksInvalidArgument("encrypted1 and encrypted2 parameter mismatch")
+        if dup.scale != acc.scale:
+            raise capi.CkksInvalidArgument("scale mismatch")
+        scratch = dup.like() if scratch is None else scratch
+        scratch.limbs, scratch.scale = dup.limbs, dup.scale
+        va, vb, vc = dup.view(), scratch.view(), acc.view()
+        where = C.c_int(0)
+        check(self.lib.ckks_rotate_sum_chain(self.h, keys._h, C.byref(va), C.byref(vb), C.byref(vc), int(steps), int(count),
+                                             C.byref(where), _stream()))
+        return scratch if where.value else dup
+
     def multiply_plain_sum(self, cts, pts, out=None):
         """multiply_plain of every batch entry with its plaintext, then add_many, in one kernel"""
         if cts.limbs != pts.limbs or cts.batch != pts.batch:

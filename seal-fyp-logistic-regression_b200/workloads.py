@@ -180,11 +180,8 @@ def cipher_dot_product(ev, ctA, ctB, size, keys):
     mult = ev.relinearize(mult, keys)
     ev.rescale_to_next_inplace(mult)
     dup = ev.add(mult, ev.rotate_vector(mult, -size, keys))      # "vector has duplicate now"
-    nxt = dup.like()
-    for _ in range(1, size):
-        ev.rotate_vector(dup, 1, keys, out=nxt)                   # rotate_vector_inplace(dup, 1)
-        dup, nxt = nxt, dup
-        ev.add_inplace(mult, dup)
+    # for i in 1..size-1: rotate_vector_inplace(dup, 1); add_inplace(mult, dup)   (helper.h:472-476)
+    ev.rotate_sum_chain(dup, mult, 1, size - 1, keys)
     return force_scale_pow2(mult)
 
 
