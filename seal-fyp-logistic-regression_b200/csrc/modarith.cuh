@@ -23,19 +23,40 @@ struct ModConst {
     u64 p4hi;   // high 32 bits of 4p (threshold of the cheap lazy correction)
 };
 
-// truncated high product: floor(a*b / 2^64) - e with e in {0,1,2}.  Three multiplies instead of
-// four and no carry chain; the Shoup remainder absorbs the error (range [0,4p) instead of [0,2p)).
-__device__ __forceinline__ u64 mulhi_trunc(u64 a, u64 b) {
-    const unsigned a0 = (unsigned)a, a1 = (unsigned)(a >> 32), b0 = (unsigned)b, b1 = (unsigned)(b >> 32);
-    u64 r = (u64)a1 * b1;
-    r += (u64)__umulhi(a1, b0) + (u64)__umulhi(a0, b1);
-    return r;
-}
-
-// w*x mod p, lazily reduced to [0,4p); ws = floor(w * 2^64 / p), any 64-bit x, w < p
+// w*x mod p, lazily reduced to [0,4p); ws = floor(w * 2^64 / p), any 64-bit x, w < p.
+// Written as one PTX sequence of 9 integer multiply-adds (the multiplier pipe is the binding
+// resource):
+//   q = truncated high product of ws*x: a1*b1 + hi32(a1*b0) + hi32(a0*b1) -- at most 2 below the
+//       true floor(ws*x / 2^64); the Shoup remainder absorbs the error ([0,4p) instead of [0,2p))
+//   r = low 64 bits of w*x + q*negp,  negp = 2^64 - p
 __device__ __forceinline__ u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 negp) {
-    u64 q = mulhi_trunc(ws, x);
-    return w * x + q * negp;
+    const unsigned x0 = (unsigned)x, x1 = (unsigned)(x >> 32);
+    const unsigned w0 = (unsigned)w, w1 = (unsigned)(w >> 32);
+    const unsigned s0 = (unsigned)ws, s1 = (unsigned)(ws >> 32);
+    const unsigned n0 = (unsigned)negp, n1 = (unsigned)(negp >> 32);
+    unsigned rlo, rhi;
+    asm("{\n\t"
+        ".reg .u32 q0, q1, tl, th;\n\t"
+        ".reg .u64 t;\n\t"
+        "mul.wide.u32    t, %3, %7;\n\t"          // s1*x1
+        "mov.b64         {q0, q1}, t;\n\t"
+        "mad.hi.cc.u32   q0, %3, %6, q0;\n\t"     // + hi32(s1*x0)
+        "addc.u32        q1, q1, 0;\n\t"
+        "mad.hi.cc.u32   q0, %2, %7, q0;\n\t"     // + hi32(s0*x1)
+        "addc.u32        q1, q1, 0;\n\t"
+        "mul.wide.u32    t, %4, %6;\n\t"          // w0*x0
+        "mad.wide.u32    t, q0, %8, t;\n\t"       // + q0*n0
+        "mov.b64         {tl, th}, t;\n\t"
+        "mad.lo.u32      th, %4, %7, th;\n\t"     // + (w0*x1) << 32
+        "mad.lo.u32      th, %5, %6, th;\n\t"     // + (w1*x0) << 32
+        "mad.lo.u32      th, q0, %9, th;\n\t"     // + (q0*n1) << 32
+        "mad.lo.u32      th, q1, %8, th;\n\t"     // + (q1*n0) << 32
+        "mov.u32         %0, tl;\n\t"
+        "mov.u32         %1, th;\n\t"
+        "}"
+        : "=r"(rlo), "=r"(rhi)
+        : "r"(s0), "r"(s1), "r"(w0), "r"(w1), "r"(x0), "r"(x1), "r"(n0), "r"(n1));
+    return ((u64)rhi << 32) | rlo;
 }
 // exact variant, [0,2p)
 __device__ __forceinline__ u64 shoup_lazy2(u64 x, u64 w, u64 ws, u64 p) {
