@@ -341,6 +341,15 @@ def run_gpu(args):
         return ms, res, ctx.launch_count(), t0, t1
 
     sampler = ClockSampler(local) if rank == 0 else None
+    if args.ncu:
+        for _ in range(args.warmup):
+            epoch_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()       # ncu --profile-from-start off: capture the timed region only
+        epoch_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     ms, (grad, neww), launches, t0, t1 = timed(epoch_resident, args.warmup, args.steps)
     clocks = sampler.stop(t0, t1) if sampler else None
     value = world * args.steps / (ms / 1e3)
@@ -381,8 +390,13 @@ def run_gpu(args):
     alg = nb * ks_bytes(Lk, ctx.n)
     peak, peak_src = peaks()
     achieved = alg / (ks_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "keyswitch_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("bytes_per_launch_group")
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "binding_resource": "integer multiply pipe (fmaheavy 48-70% busy per kernel, ncu) -- see DESIGN.md section 4",
         "kernel": "Galois key switch pipeline (k_ks_intt_row, k_inv_col, k_ks_modup_col, k_ks_mac, k_inv_row, "
                   "k_inv_col, k_md_fwd_col, k_md_fwd_row), batch %d, N=32768, L=%d" % (nb, Lk),
         "algorithmic_bytes_per_launch_group": alg, "ms_per_launch_group": ks_ms, "peak_source": peak_src,
@@ -468,6 +482,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the key-switch ops/s sweep")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--ncu", action="store_true", help="profiling run: one epoch between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

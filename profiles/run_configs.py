@@ -1,0 +1,135 @@
+"""Times the BASELINE.json configurations other than the bench workload on one B200 and writes
+profiles/r01_configs.json (GPU wall times with CUDA events, after warm-up; decrypted results checked
+against plaintext math).  usage: python profiles/run_configs.py [--skip-matmul64]"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "seal-fyp-logistic-regression_b200"
+pkg = importlib.import_module(PKG)
+eng = pkg.load_engine()
+params = importlib.import_module(PKG + ".params")
+client = importlib.import_module(PKG + ".client")
+wl = importlib.import_module(PKG + ".workloads")
+SCALE = 2.0 ** 40
+
+
+def timed(fn, reps=3, warm=1):
+    for _ in range(warm):
+        out = fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def setup(log_n, bits, steps, seed=1):
+    ctx = eng.Context(log_n, params.coeff_modulus_create(log_n, bits))
+    ev = eng.Evaluator(ctx)
+    enc = client.CKKSEncoder(ctx)
+    kg = client.KeyGenerator(ctx, seed=seed)
+    keys = kg.keyset(steps=steps)
+    encr = client.Encryptor(ctx, kg.public_key(), seed=seed + 1)
+    decr = client.Decryptor(ctx, kg.secret_key())
+    return ctx, ev, enc, keys, encr, decr
+
+
+def config3(results):
+    pow2 = [s for i in range(13) for s in (1 << i, -(1 << i))]
+    ctx, ev, enc, keys, encr, decr = setup(14, [60, 40, 40, 60], pow2)
+    plans = wl.PlanCache(ctx, keys)
+    rng = np.random.default_rng(3)
+    for d in (64, 128):
+        U, v = rng.uniform(0, 1, (d, d)), rng.uniform(0, 1, d)
+        ct = encr.encrypt(enc.encode(v, SCALE))
+        diags = enc.encode(wl.all_diagonals(U), SCALE)
+        ms, out = timed(lambda: wl.linear_transform_plain(ev, ct, diags, keys, plans))
+        err = float(np.abs(enc.decode(decr.decrypt(out))[0, :d] - U @ v).max())
+        ks = plans.get(range(d)).keyswitches + 1
+        results["config3_linear_transform_d%d_N16384" % d] = {"ms": ms, "key_switches": ks, "max_abs_err": err}
+        print("config3 d=%d: %.2f ms (%d key switches), err %.2e" % (d, ms, ks, err), flush=True)
+
+
+def config4(results, d):
+    pow2 = [s for i in range(13) for s in (1 << i, -(1 << i))]
+    ctx, ev, enc, keys, encr, decr = setup(14, [60, 40, 40, 40, 40, 60], pow2, seed=5)
+    plans = wl.PlanCache(ctx, keys)
+    rng = np.random.default_rng(4)
+    A, B = rng.uniform(0, 1, (d, d)), rng.uniform(0, 1, (d, d))
+    eps = 1e-8
+    t0 = time.time()
+    mk = lambda U: wl.DiagonalSet.from_matrix(U, eps, SCALE, enc)
+    sigma, tau = mk(wl.u_sigma(d)), mk(wl.u_tau(d))
+    V = [mk(wl.v_k(d, k)) for k in range(1, d)]
+    W = [mk(wl.w_k(d, k)) for k in range(1, d)]
+    t_diag = time.time() - t0
+    ctA = encr.encrypt(enc.encode(A.reshape(-1), SCALE))     # already in C_Matrix_Encode (row-major) form
+    ctB = encr.encrypt(enc.encode(B.reshape(-1), SCALE))
+    ms, out = timed(lambda: wl.cc_matrix_multiplication_sparse(ev, ctA, ctB, d, sigma, tau, V, W, keys, plans), reps=1, warm=1)
+    got = enc.decode(decr.decrypt(out))[0, : d * d].reshape(d, d)
+    err = float(np.abs(got - A @ B).max())
+    ks = 4 * (plans.get(range(d * d)).keyswitches + 1)
+    results["config4_matrix_multiplication_d%d_N16384" % d] = {
+        "ms": ms, "galois_key_switches": ks, "reference_key_switches": (2 + 2 * (d - 1)) * (ks // 4),
+        "max_abs_err": err, "host_diagonal_setup_s": t_diag}
+    print("config4 d=%d: %.1f ms (%d key switches on device; the reference performs %d), err %.2e" % (
+        d, ms, ks, (2 + 2 * (d - 1)) * (ks // 4), err), flush=True)
+
+
+def config2(results):
+    for log_n in (12, 13, 14):
+        primes = params.bfv_default(log_n)
+        ctx = eng.Context(log_n, primes)
+        ev = eng.Evaluator(ctx)
+        keys = client.KeyGenerator(ctx, seed=2).keyset(steps=[1, -1, -4, 16])
+        L = ctx.top_limbs
+        for batch in (1, 1024):
+            a = ctx.empty(batch, 2, L)
+            a.data.random_(0, 1 << 35)
+            b = a.clone()
+            pt = ctx.empty(1, 1, L)
+            pt.data.random_(0, 1 << 35)
+            a3 = ctx.empty(batch, 3, L)
+            a3.data.random_(0, 1 << 35)
+            o2, o3, sc = a.like(), a3.like(), a.like()
+            ops = {
+                "multiply_plain": lambda: ev.multiply_plain(a, pt, out=o2),
+                "multiply+relinearize": lambda: ev.relinearize(ev.multiply(a, b, out=o3), keys, out=o2),
+                "rotate_vector(1)": lambda: ev.rotate_vector(a, 1, keys, out=o2),
+                "rotate_vector(11)": lambda: ev.rotate_vector(a, 11, keys, out=o2, scratch=sc),
+                "rescale_to_next": lambda: ev.rescale_to_next(a, out=o2),
+            }
+            for name, fn in ops.items():
+                a.scale = b.scale = pt.scale = a3.scale = 1.0
+                ms, _ = timed(fn, reps=10, warm=2)
+                results.setdefault("config2_op_sweep", {})["N=%d,L=%d,batch=%d,%s" % (ctx.n, L, batch, name)] = {
+                    "us_per_call": ms * 1e3, "ops_per_s": batch / (ms * 1e-3)}
+        print("config2 N=%d done" % ctx.n, flush=True)
+
+
+def main():
+    results = {}
+    config2(results)
+    config3(results)
+    config4(results, 5)
+    if "--skip-matmul64" not in sys.argv:
+        config4(results, 64)
+    out = os.path.join(ROOT, "gpurun_out", "r01_configs.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    json.dump(results, open(out, "w"), indent=1)
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

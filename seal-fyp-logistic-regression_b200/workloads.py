@@ -246,3 +246,67 @@ def tree_cipher(ev, x, coeffs, scale, keys, encoder, encryptor):
         temp.scale = float(2.0 ** int(math.log2(enc_result.scale)))
         ev.add_inplace(enc_result, temp)
     return enc_result
+
+
+# ------------------------------------------------------------------ diagonal sets with a shared default
+class DiagonalSet:
+    """The plaintext diagonals of one matrix in de-duplicated form: `default` is the plaintext shared
+    by most diagonals (the drivers add epsilon = 1e-8 to every entry, so the diagonals of a
+    permutation matrix that would be zero all encode the same all-epsilon vector,
+    matrix_multiplication.cpp:239-246), `index`/`special` list the diagonals that differ.
+    sum_l diag_l (.) rot_l  =  default (.) (sum_all rot - sum_special rot) + sum_special diag_l (.) rot_l
+    holds exactly modulo every prime, so the result is bit-identical to the dense evaluation while
+    the d^2 x (d^2 plaintexts) of CC_Matrix_Multiplication at d = 64 (344 GB dense) never exist."""
+
+    def __init__(self, n, default, index, special):
+        self.n, self.default, self.index, self.special = n, default, list(index), special
+
+    @staticmethod
+    def from_matrix(U, eps, scale, encoder, limbs=None):
+        n = U.shape[0]
+        diags = all_diagonals(U)
+        idx = [l for l in range(n) if np.any(diags[l] != 0.0)]
+        default = encoder.encode(np.full(n, eps), scale, limbs=limbs)
+        special = encoder.encode(diags[idx] + eps, scale, limbs=limbs)
+        return DiagonalSet(n, default, idx, special)
+
+
+def linear_transform_plain_sparse(ev, ct, dset, keys, plans, rots=None, s_all=None):
+    """Linear_Transform_Plain (helper.h:237-262) for a DiagonalSet; bit-identical to the dense form"""
+    d = dset.n
+    if rots is None:
+        rots = rotations_of(ev, duplicate_fill(ev, ct, d, keys), d, plans)
+    if s_all is None:
+        s_all = ev.add_many(rots)
+    sel_idx = torch.tensor(dset.index, device=rots.data.device)
+    sel = Ciphertext(rots.ctx, rots.data.index_select(0, sel_idx), rots.limbs, rots.scale)
+    rest = ev.sub(s_all, ev.add_many(sel))
+    out = ev.multiply_plain(rest, dset.default)
+    return ev.add(out, ev.multiply_plain_sum(sel, dset.special))
+
+
+def cc_matrix_multiplication_sparse(ev, ctA, ctB, d, sigma, tau, V, W, keys, plans):
+    """CC_Matrix_Multiplication with DiagonalSets (sigma, tau, V[k], W[k]); same op sequence and
+    bit-identical result as cc_matrix_multiplication, feasible at d = 64 (d^2 = 4096 = N/4)"""
+    dd = d * d
+    A0 = linear_transform_plain_sparse(ev, ctA, sigma, keys, plans)
+    B0 = linear_transform_plain_sparse(ev, ctB, tau, keys, plans)
+    rotA = rotations_of(ev, duplicate_fill(ev, A0, dd, keys), dd, plans)
+    sA = ev.add_many(rotA)
+    A = [linear_transform_plain_sparse(ev, None, V[k], keys, plans, rots=rotA, s_all=sA) for k in range(d - 1)]
+    del rotA
+    rotB = rotations_of(ev, duplicate_fill(ev, B0, dd, keys), dd, plans)
+    sB = ev.add_many(rotB)
+    B = [linear_transform_plain_sparse(ev, None, W[k], keys, plans, rots=rotB, s_all=sB) for k in range(d - 1)]
+    del rotB
+    Ak, Bk = _stack(A), _stack(B)
+    ev.rescale_to_next_inplace(Ak)
+    ev.rescale_to_next_inplace(Bk)
+    ctAB = ev.multiply(A0, B0)
+    ev.mod_switch_to_next_inplace(ctAB)
+    force_scale_pow2(Ak)
+    force_scale_pow2(Bk)
+    rest = ev.multiply_sum(Ak, Bk)
+    if rest.scale != ctAB.scale:
+        raise capi.CkksInvalidArgument("scale mismatch")
+    return ev.add(ctAB, rest)

@@ -277,3 +277,33 @@ def test_column_layout_epoch_matches_plaintext(make_fixture):
     neww = lr.apply_gradient(ev, grad, wct, 0.1, R, scale, enc)
     got = enc.decode(decr.decrypt(neww))[0, :C]
     assert np.abs(got - lr.plain_epoch(X, y, w0, 0.1, degree)).max() < 1e-3
+
+
+def test_sparse_diagonal_sets_match_dense(make_fixture):
+    """the de-duplicated diagonal evaluation (needed for CC_Matrix_Multiplication at d = 64) is
+    bit-identical to the dense one"""
+    wl, _, _ = _mods()
+    fx = make_fixture(12, [50, 40, 40, 40, 40, 50], steps=POW2)
+    br = Bridge(fx)
+    plans = wl.PlanCache(fx.ctx, fx.keys)
+    rng = np.random.default_rng(8)
+    scale, eps, d = 2.0 ** 40, 1e-8, 3
+    A, B = rng.uniform(0, 1, (d, d)), rng.uniform(0, 1, (d, d))
+    ctA = fx.ctx.upload(_enc(fx, 500, A.reshape(-1), scale), scale=scale)
+    ctB = fx.ctx.upload(_enc(fx, 501, B.reshape(-1), scale), scale=scale)
+
+    def dense(U):
+        return br.encode(wl.all_diagonals(U) + eps, scale)
+
+    def sparse(U):
+        return wl.DiagonalSet.from_matrix(U, eps, scale, br)
+
+    mats = dict(sigma=wl.u_sigma(d), tau=wl.u_tau(d), V=[wl.v_k(d, k) for k in range(1, d)], W=[wl.w_k(d, k) for k in range(1, d)])
+    want = wl.cc_matrix_multiplication(fx.ev, ctA, ctB, d, dense(mats["sigma"]), dense(mats["tau"]),
+                                       [dense(m) for m in mats["V"]], [dense(m) for m in mats["W"]], fx.keys, plans)
+    got = wl.cc_matrix_multiplication_sparse(fx.ev, ctA, ctB, d, sparse(mats["sigma"]), sparse(mats["tau"]),
+                                             [sparse(m) for m in mats["V"]], [sparse(m) for m in mats["W"]], fx.keys, plans)
+    assert got.limbs == want.limbs and got.scale == want.scale
+    assert np.array_equal(got.numpy(), want.numpy())
+    dec = fx.orc.decode(fx.orc.decrypt(fx.sk, got.numpy()[0]), got.scale)[: d * d].reshape(d, d)
+    assert np.abs(dec - A @ B).max() < 1e-3
