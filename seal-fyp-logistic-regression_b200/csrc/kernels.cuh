@@ -213,8 +213,14 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ks_modup_col(const u64 *__restr
     const ModConst m = load_mod(t, pj);
     const int c0 = blockIdx.x * 32;
     u64 x[8];
+    // SEAL reduces the digit modulo q_j only when q_i > q_j; the transform itself accepts any value
+    // below 8 q_j, so the Barrett reduction is needed only for a much larger source prime
+    const bool need_reduce = t.mod[i].p >= m.p4;
 #pragma unroll
-    for (int e = 0; e < 8; e++) x[e] = reduce64(in[col_coarse_idx<LOGN>(c0, e)], m);
+    for (int e = 0; e < 8; e++) {
+        u64 v = in[col_coarse_idx<LOGN>(c0, e)];
+        x[e] = need_reduce ? reduce64(v, m) : v;
+    }
     fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, smem);
 #pragma unroll
     for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
@@ -300,8 +306,12 @@ __global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_col(DView R, u64 *T2, in
     const u64 hm = t.round_half ? t.halfmod[a * t.K + j] : 0;
     const int c0 = blockIdx.x * 32;
     u64 x[8];
+    const bool need_reduce = t.mod[a].p >= m.p4;   // else r' + q_j - hm < 8 q_j is already a valid lazy input
 #pragma unroll
-    for (int e = 0; e < 8; e++) x[e] = submod(reduce64(in[col_coarse_idx<LOGN>(c0, e)], m), hm, m.p);
+    for (int e = 0; e < 8; e++) {
+        u64 v = in[col_coarse_idx<LOGN>(c0, e)];
+        x[e] = need_reduce ? submod(reduce64(v, m), hm, m.p) : v + m.p - hm;
+    }
     fwd_col_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, smem);
 #pragma unroll
     for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
@@ -345,10 +355,14 @@ __global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_row(const u64 *__restric
             for (int e = 0; e < 8; e++) bv[e] = bp[ix[e]];
         }
     }
+    // (minuend - NTT(u)) * q_a^-1 without canonicalising the transform output first: the lazy value
+    // (< 8p + 2^32) is subtracted from minuend + 9p (a multiple of p, no underflow), one truncated
+    // Shoup multiply brings the product to [0,4p), two conditional subtractions make it canonical
+    const u64 p9 = m.p4 + m.p4 + m.p;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-        u64 v = reduce64(x[e], m);
-        u64 r = shoup_mul(submod(mv[e], v, m.p), qi, qis, m.p);
+        u64 r = shoup_lazy(mv[e] + p9 - x[e], qi, qis, m.negp);
+        r = csub(csub(r, m.p2), m.p);
         if (MODE == 1 || (MODE == 2 && s == 0)) r = addmod(r, bv[e], m.p);
         x[e] = r;
     }
