@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_row(DView src, DView dst, i
 }
 
 template <int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS) k_inv_row(DView src, DView dst, int limbs, int first_prime, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 5) k_inv_row(DView src, DView dst, int limbs, int first_prime, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int s = blockIdx.y / limbs, l = blockIdx.y % limbs, pj = first_prime + l;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_inv_col(DView src, DView dst, i
 // permutation out[g] = in[perm[g]] (SEAL util::apply_galois_ntt); perm maps each row of the
 // limb matrix into a single source row, so the gather stays inside one 0.5-4 KB segment.
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS) k_ks_intt_row(KsRoute rt, u64 *D, int L, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_intt_row(KsRoute rt, u64 *D, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int i = blockIdx.y, b = blockIdx.z;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ks_intt_row(KsRoute rt, u64 *D,
 // (3) mod-up, column pass: digit i (coefficient form, canonical) reduced into prime pj and pushed
 // through the first six NTT stages.  y = i*(L+1) + jj; jj == L is the special prime.
 template <int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS) k_ks_modup_col(const u64 *__restrict__ D, u64 *T1, int L, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *__restrict__ D, u64 *T1, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int i = blockIdx.y / (L + 1), jj = blockIdx.y % (L + 1), b = blockIdx.z;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *__restrict
 // instance z; the value is carried into prime j as (r' mod q_j) - (half mod q_j) and pushed
 // through the first six NTT stages.  R limb of instance z: R.data + z*R.bs.
 template <int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_col(DView R, u64 *T2, int Lout, int a, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 5) k_md_fwd_col(DView R, u64 *T2, int Lout, int a, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int j = blockIdx.y, z = blockIdx.z;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_col(DView R, u64 *T2, in
 // base = permuted in[b][0] for k == 0 and nothing for k == 1 (SEAL wipes c1 before switching).
 // z = b*S + s enumerates (ciphertext, poly).
 template <int LOGN, int MODE>
-__global__ void __launch_bounds__(NTT_THREADS) k_md_fwd_row(const u64 *__restrict__ T2, DView minuend, KsRoute rt, int S, int Lout, int a, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *__restrict__ T2, DView minuend, KsRoute rt, int S, int Lout, int a, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int j = blockIdx.y, z = blockIdx.z, b = z / S, s = z % S;
