@@ -22,6 +22,8 @@ reps = int(sys.argv[5]) if len(sys.argv) > 5 else 20
 
 primes = params.coeff_modulus_create(log_n, [60] + [40] * (top - 1) + [60])
 ctx = eng.Context(log_n, primes)
+if len(sys.argv) > 6:
+    ctx.set_workspace_cap(int(float(sys.argv[6]) * (1 << 20)))
 ev = eng.Evaluator(ctx)
 keys = client.KeyGenerator(ctx, seed=1).keyset(steps=[1])
 a = ctx.empty(batch, 2, L, cap=top)

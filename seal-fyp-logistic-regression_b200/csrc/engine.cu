@@ -36,6 +36,25 @@ static int fail(int code, const std::string &msg) {
             return fail(CKKS_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
     } while (0)
 
+// Programmatic dependent launch: the next kernel of a pipeline may become resident while the
+// previous one drains; it runs its prologue (constants, first twiddles) and blocks at
+// griddepcontrol.wait until the predecessor's memory is visible.  Hides launch ramp-up between the
+// eight kernels of a key switch.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NTT_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------------------------ context
 struct ckks_ctx {
     int log_n = 0, n = 0, K = 0, device = 0;
@@ -429,7 +448,7 @@ static int get_perm(ckks_ctx *c, uint64_t g, const uint32_t **out) {
 // Batched key switch over `nslots` launch slots.
 // mode 1: relinearize (target = poly 2 of the source, base = polys 0,1)
 // mode 2: Galois      (target = permuted poly 1, base = permuted poly 0)
-static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaStream_t st) {
+static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaStream_t st, bool chained = false) {
     const int K = c->K;
     const size_t N = c->n;
     const int Bc = ks_chunk(c, nslots, L);
@@ -449,24 +468,27 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
 #define RUN(LN)                                                                                                         \
     {                                                                                                                   \
         typedef NttGeo<LN> G;                                                                                           \
-        if (mode == 2) k_ks_intt_row<LN, true><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(rt, D, L, c->t);      \
-        else k_ks_intt_row<LN, false><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(rt, D, L, c->t);               \
+        /* the first kernel follows arbitrary stream work (copies, foreign kernels): ordinary launch unless  \
+           the caller chains key switches back to back */                                                      \
+        if (chained && mode == 2) launch_pdl(k_ks_intt_row<LN, true>, dim3(G::ROW_TILES, L, bc), st, rt, D, L, c->t); \
+        else if (mode == 2) k_ks_intt_row<LN, true><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(rt, D, L, c->t); \
+        else k_ks_intt_row<LN, false><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(rt, D, L, c->t);       \
         LAUNCH_CHECK(c);                                                                                                \
-        k_inv_col<LN, false><<<dim3(G::COL_TILES, L, bc), NTT_THREADS, 0, st>>>(dD, dD, L, 0, c->t);                    \
+        launch_pdl(k_inv_col<LN, false>, dim3(G::COL_TILES, L, bc), st, dD, dD, L, 0, c->t);                    \
         LAUNCH_CHECK(c);                                                                                                \
-        k_ks_modup_col<LN><<<dim3(G::COL_TILES, L *(L + 1), bc), NTT_THREADS, 0, st>>>(D, T1, L, c->t);                 \
+        launch_pdl(k_ks_modup_col<LN>, dim3(G::COL_TILES, L *(L + 1), bc), st, D, T1, L, c->t);                 \
         LAUNCH_CHECK(c);                                                                                                \
-        if (mode == 2) k_ks_mac<LN, true><<<dim3(G::ROW_TILES, L + 1, bc), NTT_THREADS, 0, st>>>(T1, rt, ACC, L, c->t); \
-        else k_ks_mac<LN, false><<<dim3(G::ROW_TILES, L + 1, bc), NTT_THREADS, 0, st>>>(T1, rt, ACC, L, c->t);          \
+        if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, L + 1, bc), st, T1, rt, ACC, L, c->t); \
+        else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, L + 1, bc), st, T1, rt, ACC, L, c->t);          \
         LAUNCH_CHECK(c);                                                                                                \
-        k_inv_row<LN><<<dim3(G::ROW_TILES, 1, 2 * bc), NTT_THREADS, 0, st>>>(spec, spec, 1, K - 1, c->t);               \
+        launch_pdl(k_inv_row<LN>, dim3(G::ROW_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);               \
         LAUNCH_CHECK(c);                                                                                                \
-        k_inv_col<LN, true><<<dim3(G::COL_TILES, 1, 2 * bc), NTT_THREADS, 0, st>>>(spec, spec, 1, K - 1, c->t);         \
+        launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);         \
         LAUNCH_CHECK(c);                                                                                                \
-        k_md_fwd_col<LN><<<dim3(G::COL_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(spec, T2, L, K - 1, c->t);              \
+        launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, L, 2 * bc), st, spec, T2, L, K - 1, c->t);              \
         LAUNCH_CHECK(c);                                                                                                \
-        if (mode == 2) k_md_fwd_row<LN, 2><<<dim3(G::ROW_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(T2, minu, rt, 2, L, K - 1, c->t); \
-        else k_md_fwd_row<LN, 1><<<dim3(G::ROW_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(T2, minu, rt, 2, L, K - 1, c->t); \
+        if (mode == 2) launch_pdl(k_md_fwd_row<LN, 2>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
+        else launch_pdl(k_md_fwd_row<LN, 1>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
         LAUNCH_CHECK(c);                                                                                                \
     }
         DISPATCH_LOGN(c, RUN)
@@ -605,11 +627,11 @@ extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const c
     const int L = a->limbs, B = a->batch;
     if ((rc = ensure_ws(c, ks_words_per_ct(c, L) * 8 * (size_t)ks_chunk(c, B, L)))) return rc;
     cudaStream_t user = (cudaStream_t)s;
-    auto one = [&](const ckks_view *src, const ckks_view *dst, cudaStream_t st) -> int {
+    auto one = [&](const ckks_view *src, const ckks_view *dst, cudaStream_t st, bool chained) -> int {
         KsRoute rt = uniform_route(src, dst, perm, it->second);
         rt.accv = dv(acc);
         rt.has_acc = 1;
-        return keyswitch(c, 2, L, B, rt, st);
+        return keyswitch(c, 2, L, B, rt, st, chained);
     };
     int done = 0;
     if (count >= 4) {
@@ -626,8 +648,8 @@ extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const c
             cudaGraph_t graph = nullptr;
             uint64_t before = c->launches;
             CU(cudaStreamBeginCapture(c->chain_stream, cudaStreamCaptureModeThreadLocal));
-            rc = one(a, b, c->chain_stream);
-            if (!rc) rc = one(b, a, c->chain_stream);
+            rc = one(a, b, c->chain_stream, false);
+            if (!rc) rc = one(b, a, c->chain_stream, true);
             cudaError_t ce = cudaStreamEndCapture(c->chain_stream, &graph);
             uint64_t per = c->launches - before;
             c->launches = before;
@@ -655,7 +677,7 @@ extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const c
     }
     const ckks_view *src = a, *dst = b;
     for (; done < count; done++) {
-        if ((rc = one(src, dst, user))) return rc;
+        if ((rc = one(src, dst, user, false))) return rc;
         const ckks_view *t = src;
         src = dst;
         dst = t;
@@ -860,11 +882,11 @@ extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *o
         typedef NttGeo<LN> G;                                                                                     \
         k_inv_row<LN><<<dim3(G::ROW_TILES, S, bc), NTT_THREADS, 0, st>>>(last, dR, 1, Lo, c->t);                  \
         LAUNCH_CHECK(c);                                                                                          \
-        k_inv_col<LN, true><<<dim3(G::COL_TILES, S, bc), NTT_THREADS, 0, st>>>(dR, dR, 1, Lo, c->t);              \
+        launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, S, bc), st, dR, dR, 1, Lo, c->t);              \
         LAUNCH_CHECK(c);                                                                                          \
-        k_md_fwd_col<LN><<<dim3(G::COL_TILES, Lo, bc * S), NTT_THREADS, 0, st>>>(Rz, T2, Lo, Lo, c->t);           \
+        launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, Lo, bc * S), st, Rz, T2, Lo, Lo, c->t);           \
         LAUNCH_CHECK(c);                                                                                          \
-        k_md_fwd_row<LN, 0><<<dim3(G::ROW_TILES, Lo, bc * S), NTT_THREADS, 0, st>>>(T2, src, rrt, S, Lo, Lo, c->t); \
+        launch_pdl(k_md_fwd_row<LN, 0>, dim3(G::ROW_TILES, Lo, bc * S), st, T2, src, rrt, S, Lo, Lo, c->t); \
         LAUNCH_CHECK(c);                                                                                          \
     }
         DISPATCH_LOGN(c, RUN)

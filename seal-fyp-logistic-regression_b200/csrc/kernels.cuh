@@ -54,6 +54,10 @@ __device__ __forceinline__ void load_perm8(unsigned (&ix)[8], const uint32_t *pe
     ix[0] = a.x; ix[1] = a.y; ix[2] = a.z; ix[3] = a.w;
     ix[4] = b.x; ix[5] = b.y; ix[6] = b.z; ix[7] = b.w;
 }
+// programmatic dependent launch (sm_90+): let the successor start its prologue / wait for the
+// predecessor's results
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Per-entry routing of a batched key switch: which ciphertext of the views a launch slot works
@@ -132,12 +136,14 @@ template <int LOGN>
 __global__ void __launch_bounds__(NTT_THREADS, 5) k_inv_row(DView src, DView dst, int limbs, int first_prime, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
+    pdl_launch_dependents();
     const int s = blockIdx.y / limbs, l = blockIdx.y % limbs, pj = first_prime + l;
     const u64 *in = src.data + blockIdx.z * src.bs + s * src.ps + (u64)l * G::N;
     u64 *out = dst.data + blockIdx.z * dst.bs + s * dst.ps + (u64)l * G::N;
     const ModConst m = load_mod(t, pj);
     const int t0 = blockIdx.x * NTT_TILE;
     u64 x[8];
+    pdl_wait();
     load8(x, in + t0 + 8 * threadIdx.x);
     inv_row_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m, t0, smem);
 #pragma unroll
@@ -150,12 +156,14 @@ template <int LOGN, bool ADD_HALF>
 __global__ void __launch_bounds__(NTT_THREADS) k_inv_col(DView src, DView dst, int limbs, int first_prime, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
+    pdl_launch_dependents();
     const int s = blockIdx.y / limbs, l = blockIdx.y % limbs, pj = first_prime + l;
     const u64 *in = src.data + blockIdx.z * src.bs + s * src.ps + (u64)l * G::N;
     u64 *out = dst.data + blockIdx.z * dst.bs + s * dst.ps + (u64)l * G::N;
     const ModConst m = load_mod(t, pj);
     const int c0 = blockIdx.x * 32;
     u64 x[8];
+    pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[col_fine_idx<LOGN>(c0, e)];
     inv_col_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m, smem);
@@ -177,6 +185,7 @@ template <int LOGN, bool GALOIS>
 __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_intt_row(KsRoute rt, u64 *D, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
+    pdl_launch_dependents();
     const int i = blockIdx.y, b = blockIdx.z;
     const KsSel sl = route_sel(rt, b);
     const DView tgt = rt.v[sl.src];
@@ -188,10 +197,12 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_intt_row(KsRoute rt, u64 
     u64 x[8];
     if (GALOIS) {
         unsigned ix[8];
-        load_perm8(ix, perm + t0 + 8 * threadIdx.x);
+        load_perm8(ix, perm + t0 + 8 * threadIdx.x);   // static table: before the dependency wait
+        pdl_wait();
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = in[ix[e]];
     } else {
+        pdl_wait();
         load8(x, in + t0 + 8 * threadIdx.x);
     }
     inv_row_pass<LOGN>(x, t.twi + (size_t)i * G::N, m, t0, smem);
@@ -202,9 +213,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_intt_row(KsRoute rt, u64 
 // (3) mod-up, column pass: digit i (coefficient form, canonical) reduced into prime pj and pushed
 // through the first six NTT stages.  y = i*(L+1) + jj; jj == L is the special prime.
 template <int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *__restrict__ D, u64 *T1, int L, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *D, u64 *T1, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
+    pdl_launch_dependents();
     const int i = blockIdx.y / (L + 1), jj = blockIdx.y % (L + 1), b = blockIdx.z;
     const int pj = jj == L ? t.K - 1 : jj;
     if (pj == i) return;  // that limb is taken directly from the NTT-form target
@@ -216,6 +228,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *__re
     // SEAL reduces the digit modulo q_j only when q_i > q_j; the transform itself accepts any value
     // below 8 q_j, so the Barrett reduction is needed only for a much larger source prime
     const bool need_reduce = t.mod[i].p >= m.p4;
+    pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         u64 v = in[col_coarse_idx<LOGN>(c0, e)];
@@ -230,9 +243,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *__re
 //     acc_k = sum_i NTT_pj(digit_i) (.) ksk[i][k][pj]     (k = 0,1), 128-bit lazy sums,
 // one Barrett reduction at the end.  Key limbs stream once from HBM, fully coalesced.
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *__restrict__ T1, KsRoute rt, u64 *ACC, int L, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRoute rt, u64 *ACC, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
+    pdl_launch_dependents();
     const int jj = blockIdx.y, b = blockIdx.z;
     const KsSel sl = route_sel(rt, b);
     const DView tgt = rt.v[sl.src];
@@ -245,6 +259,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *__restrict
     u64 lo0[8], hi0[8], lo1[8], hi1[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) lo0[e] = hi0[e] = lo1[e] = hi1[e] = 0;
+    pdl_wait();
     for (int i = 0; i < L; i++) {
         u64 x[8];
         // the key stream comes from HBM: start it before the transform of this digit
@@ -299,6 +314,7 @@ template <int LOGN>
 __global__ void __launch_bounds__(NTT_THREADS, 5) k_md_fwd_col(DView R, u64 *T2, int Lout, int a, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
+    pdl_launch_dependents();
     const int j = blockIdx.y, z = blockIdx.z;
     const u64 *in = R.data + z * R.bs;
     u64 *out = T2 + ((u64)z * Lout + j) * G::N;
@@ -307,6 +323,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_md_fwd_col(DView R, u64 *T2,
     const int c0 = blockIdx.x * 32;
     u64 x[8];
     const bool need_reduce = t.mod[a].p >= m.p4;   // else r' + q_j - hm < 8 q_j is already a valid lazy input
+    pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         u64 v = in[col_coarse_idx<LOGN>(c0, e)];
@@ -323,9 +340,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_md_fwd_col(DView R, u64 *T2,
 // base = permuted in[b][0] for k == 0 and nothing for k == 1 (SEAL wipes c1 before switching).
 // z = b*S + s enumerates (ciphertext, poly).
 template <int LOGN, int MODE>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *__restrict__ T2, DView minuend, KsRoute rt, int S, int Lout, int a, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *T2, DView minuend, KsRoute rt, int S, int Lout, int a, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
+    pdl_launch_dependents();
     const int j = blockIdx.y, z = blockIdx.z, b = z / S, s = z % S;
     const KsSel sl = route_sel(rt, b);
     const DView base = rt.v[sl.src], dst = rt.v[sl.dst];
@@ -335,6 +353,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *__rest
     const u64 qi = t.inv[a * t.K + j], qis = t.invs[a * t.K + j];
     const int t0 = blockIdx.x * NTT_TILE;
     u64 x[8];
+    pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
     fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, t0, smem);
