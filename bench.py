@@ -53,6 +53,14 @@ def ks_bytes(L, n, relin=False):
     return (2 * L * L + (7 if relin else 6) * L) * 8 * n
 
 
+def ks_int_mults(L, n, log_n):
+    """integer multiplies one key switch needs at minimum with this algorithm: (L^2+3L+2) NTTs of
+    (N/2) log2 N butterflies at 9 32-bit multiplies each (truncated-Shoup), the 128-bit key inner
+    product (4 per term, 2 L (L+1) N terms), its Barrett reductions and the mod-down epilogue"""
+    ntts = L * L + 3 * L + 2
+    return ntts * (n // 2) * log_n * 9 + 4 * 2 * L * (L + 1) * n + 7 * 2 * (L + 1) * n + 9 * 2 * L * n
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -402,6 +410,15 @@ def run_gpu(args):
         "algorithmic_bytes_per_launch_group": alg, "ms_per_launch_group": ks_ms, "peak_source": peak_src,
         "keyswitch_per_s": nb / (ks_ms * 1e-3),
     }
+    # second roofline (north star: "memory or integer-ALU roofline"): the integer multiplier.  ncu shows
+    # ~4 fmaheavy cycles per warp-wide IMAD/IMAD.WIDE/IMAD.HI on this part, i.e. 32 lanes/clk/SM.
+    sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+    int_peak = 148 * 32 * sm_hz * 1e6
+    mults = nb * ks_int_mults(Lk, ctx.n, LOG_N)
+    roofline["integer_multiply"] = {
+        "mults_per_launch_group": mults, "achieved_gmul_s": mults / (ks_ms * 1e-3) / 1e9, "peak_gmul_s": int_peak / 1e9,
+        "frac": mults / (ks_ms * 1e-3) / int_peak,
+        "peak_source": "148 SMs x 32 int-mul lanes/clk (fitted from ncu fmaheavy cycles) x measured SM clock"}
     ks_extra = keyswitch_sweep(torch, eng, ctx, ev, keys) if rank == 0 and not args.no_sweep else None
 
     cpu = None
