@@ -53,3 +53,45 @@ def test_shim_driver_runs_on_gpu(pkg):
     exe = build_driver()
     res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-3000:]
+
+
+REF_BUILD = os.path.join(ROOT, "tests", "cpp", "_build")
+
+
+def _run_ref(name, cwd, stdin=None, timeout=600):
+    exe = os.path.join(REF_BUILD, name)
+    if not os.path.exists(exe):
+        pytest.skip("reference binary %s was not prebuilt (needs /root/reference at build time)" % name)
+    res = subprocess.run([exe], cwd=cwd, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    assert res.returncode == 0, res.stdout[-2000:]
+    return res.stdout
+
+
+@pytest.mark.gpu
+def test_reference_matrix_mult_benchmark_runs_unmodified(pkg, tmp_path):
+    """the reference's own matrix_mult_benchmark (CC_Matrix_Multiplication, d = 5, N = 16384), built
+    unchanged against the shim, prints a decrypted product equal to its own plaintext check"""
+    import re
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    out = _run_ref("matrix_mult_benchmark", str(tmp_path))
+    got_blk = out.split("Resulting matrix:")[1].split("Expected Matrix:")[0]
+    exp_blk = out.split("Expected Matrix:")[1]
+    num = lambda t: [float(x) for x in re.findall(r"-?\d+\.\d+(?:e-?\d+)?", t)]
+    got, exp = num(got_blk)[:25], num(exp_blk)[:25]
+    assert len(got) == 25 and len(exp) == 25
+    assert max(abs(a - b) for a, b in zip(got, exp)) < 1e-3
+
+
+@pytest.mark.gpu
+def test_reference_ckks_tutorial_runs_unmodified(pkg, tmp_path):
+    """4_ckks.cpp (PI*x^3 + 0.4x + 1 with rescale / mod-switch / manual scale set)"""
+    import re
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    out = _run_ref("4_ckks", str(tmp_path))
+    exp = [float(x) for x in re.findall(r"-?\d+\.\d+", out.split("Expected result")[1].split("Computed result")[0])]
+    got = [float(x) for x in re.findall(r"-?\d+\.\d+", out.split("Computed result")[1])][: len(exp)]
+    assert len(exp) >= 6 and max(abs(a - b) for a, b in zip(got, exp)) < 1e-4
