@@ -61,6 +61,7 @@ struct ckks_ctx {
     std::vector<uint64_t> primes;
     Tables t{};
     void *d_mod = nullptr, *d_twf = nullptr, *d_twi = nullptr, *d_inv = nullptr, *d_invs = nullptr, *d_half = nullptr;
+    void *d_fp = nullptr, *d_twfd = nullptr, *d_twid = nullptr;
     std::unordered_map<uint64_t, uint32_t *> perms;
     u64 *ws = nullptr;
     size_t ws_bytes = 0;
@@ -137,7 +138,10 @@ extern "C" int ckks_ctx_create(int log_n, int n_primes, const uint64_t *primes, 
         (rc = upload_vec(&c->d_twi, ht.twi.data(), ht.twi.size() * 8)) ||
         (rc = upload_vec(&c->d_inv, ht.inv.data(), ht.inv.size() * 8)) ||
         (rc = upload_vec(&c->d_invs, ht.invs.data(), ht.invs.size() * 8)) ||
-        (rc = upload_vec(&c->d_half, ht.halfmod.data(), ht.halfmod.size() * 8))) {
+        (rc = upload_vec(&c->d_half, ht.halfmod.data(), ht.halfmod.size() * 8)) ||
+        (rc = upload_vec(&c->d_fp, ht.fpc.data(), ht.fpc.size() * 8)) ||
+        (rc = upload_vec(&c->d_twfd, ht.twfd.data(), ht.twfd.size() * 8)) ||
+        (rc = upload_vec(&c->d_twid, ht.twid.data(), ht.twid.size() * 8))) {
         ckks_ctx_destroy(c);
         return rc;
     }
@@ -147,6 +151,9 @@ extern "C" int ckks_ctx_create(int log_n, int n_primes, const uint64_t *primes, 
     c->t.inv = (const u64 *)c->d_inv;
     c->t.invs = (const u64 *)c->d_invs;
     c->t.halfmod = (const u64 *)c->d_half;
+    c->t.fp = (const FpConst *)c->d_fp;
+    c->t.twfd = (const double *)c->d_twfd;
+    c->t.twid = (const double *)c->d_twid;
     c->t.K = n_primes;
     c->t.round_half = 1;
     *out = c;
@@ -163,6 +170,7 @@ extern "C" void ckks_ctx_destroy(ckks_ctx *c) {
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     cudaFree(c->d_mod); cudaFree(c->d_twf); cudaFree(c->d_twi);
     cudaFree(c->d_inv); cudaFree(c->d_invs); cudaFree(c->d_half);
+    cudaFree(c->d_fp); cudaFree(c->d_twfd); cudaFree(c->d_twid);
     cudaFree(c->ws);
     delete c;
 }

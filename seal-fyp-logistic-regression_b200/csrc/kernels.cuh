@@ -20,6 +20,9 @@ struct Tables {
     const u64 *inv;       // [K][K]  inv[a*K+j]  = q_a^-1 mod q_j
     const u64 *invs;      // [K][K]  Shoup companion
     const u64 *halfmod;   // [K][K]  (q_a >> 1) mod q_j
+    const FpConst *fp;    // [K]     FP64-path constants (ok != 0 for primes below 2^41)
+    const double *twfd;   // [K][N]  forward twiddles as doubles
+    const double *twid;   // [K][N]  inverse twiddles as doubles
     int K;
     int round_half;
 };
@@ -31,6 +34,9 @@ struct DView {
 };
 
 __device__ __forceinline__ ModConst load_mod(const Tables &t, int j) { return t.mod[j]; }
+__device__ __forceinline__ double *as_fp(u64 *smem) { return reinterpret_cast<double *>(smem); }
+__device__ __forceinline__ double bits_fp(u64 v) { return __longlong_as_double((long long)v); }
+__device__ __forceinline__ u64 fp_bits(double v) { return (u64)__double_as_longlong(v); }
 
 // eight contiguous words of a thread (64 bytes) as four 16-byte accesses
 __device__ __forceinline__ void load8(u64 (&x)[8], const u64 *p) {
@@ -106,6 +112,16 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_col(DView src, DView dst, i
     u64 *out = dst.data + blockIdx.z * dst.bs + s * dst.ps + (u64)l * G::N;
     const ModConst m = load_mod(t, pj);
     const int c0 = blockIdx.x * 32;
+    const FpConst f = t.fp[pj];
+    if (f.ok != 0.0) {   // small prime: FP64 butterflies; the intermediate limb holds doubles
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(in[col_coarse_idx<LOGN>(c0, e)]);
+        fwd_col_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, as_fp(smem));
+#pragma unroll
+        for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = fp_bits(xd[e]);
+        return;
+    }
     u64 x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[col_coarse_idx<LOGN>(c0, e)];
@@ -124,6 +140,17 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_row(DView src, DView dst, i
     const ModConst m = load_mod(t, pj);
     const int t0 = blockIdx.x * NTT_TILE;
     u64 x[8];
+    const FpConst f = t.fp[pj];
+    if (f.ok != 0.0) {
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = bits_fp(in[t0 + row_strided_li<LOGN>(e)]);
+        fwd_row_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, t0, as_fp(smem));
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = fp_to_canonical(xd[e], f);
+        store8(out + t0 + 8 * threadIdx.x, x);
+        return;
+    }
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
     fwd_row_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, t0, smem);
@@ -143,8 +170,18 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_inv_row(DView src, DView dst
     const ModConst m = load_mod(t, pj);
     const int t0 = blockIdx.x * NTT_TILE;
     u64 x[8];
+    const FpConst f = t.fp[pj];
     pdl_wait();
     load8(x, in + t0 + 8 * threadIdx.x);
+    if (f.ok != 0.0) {
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+        inv_row_pass_fp<LOGN>(xd, t.twid + (size_t)pj * G::N, f, t0, as_fp(smem));
+#pragma unroll
+        for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = fp_bits(xd[e]);
+        return;
+    }
     inv_row_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m, t0, smem);
 #pragma unroll
     for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = x[e];  // lazy
@@ -163,11 +200,25 @@ __global__ void __launch_bounds__(NTT_THREADS) k_inv_col(DView src, DView dst, i
     const ModConst m = load_mod(t, pj);
     const int c0 = blockIdx.x * 32;
     u64 x[8];
+    const FpConst f = t.fp[pj];
+    const u64 half = (ADD_HALF && t.round_half) ? (m.p >> 1) : 0;
     pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[col_fine_idx<LOGN>(c0, e)];
+    if (f.ok != 0.0) {
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = bits_fp(x[e]);
+        inv_col_pass_fp<LOGN>(xd, t.twid + (size_t)pj * G::N, f, as_fp(smem));
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            u64 v = fp_to_canonical(xd[e], f);
+            if (ADD_HALF) v = csub(v + half, m.p);
+            out[col_coarse_idx<LOGN>(c0, e)] = v;
+        }
+        return;
+    }
     inv_col_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m, smem);
-    const u64 half = (ADD_HALF && t.round_half) ? (m.p >> 1) : 0;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         u64 v = csub(csub(x[e], m.p2), m.p);
@@ -205,6 +256,16 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_intt_row(KsRoute rt, u64 
         pdl_wait();
         load8(x, in + t0 + 8 * threadIdx.x);
     }
+    const FpConst f = t.fp[i];
+    if (f.ok != 0.0) {
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+        inv_row_pass_fp<LOGN>(xd, t.twid + (size_t)i * G::N, f, t0, as_fp(smem));
+#pragma unroll
+        for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = fp_bits(xd[e]);
+        return;
+    }
     inv_row_pass<LOGN>(x, t.twi + (size_t)i * G::N, m, t0, smem);
 #pragma unroll
     for (int e = 0; e < 8; e++) out[t0 + row_strided_li<LOGN>(e)] = x[e];
@@ -228,11 +289,21 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *D, u
     // SEAL reduces the digit modulo q_j only when q_i > q_j; the transform itself accepts any value
     // below 8 q_j, so the Barrett reduction is needed only for a much larger source prime
     const bool need_reduce = t.mod[i].p >= m.p4;
+    const FpConst f = t.fp[pj];
     pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         u64 v = in[col_coarse_idx<LOGN>(c0, e)];
         x[e] = need_reduce ? reduce64(v, m) : v;
+    }
+    if (f.ok != 0.0) {   // x < 4 q_j < 2^43: exact as doubles
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+        fwd_col_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, as_fp(smem));
+#pragma unroll
+        for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = fp_bits(xd[e]);
+        return;
     }
     fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, smem);
 #pragma unroll
@@ -255,6 +326,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
     const int K = t.K, pj = jj == L ? K - 1 : jj;
     const ModConst m = load_mod(t, pj);
     const tw_t *tw = t.twf + (size_t)pj * G::N;
+    const FpConst f = t.fp[pj];
     const int t0 = blockIdx.x * NTT_TILE;
     u64 lo0[8], hi0[8], lo1[8], hi1[8];
 #pragma unroll
@@ -280,7 +352,16 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
 #pragma unroll
             for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
             __syncthreads();  // previous iteration's shared-memory reads are done
-            fwd_row_pass<LOGN>(x, tw, m, t0, smem);
+            if (f.ok != 0.0) {
+                double xd[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) xd[e] = bits_fp(x[e]);
+                fwd_row_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, t0, as_fp(smem));
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = fp_to_canonical(xd[e], f);
+            } else {
+                fwd_row_pass<LOGN>(x, tw, m, t0, smem);
+            }
         }
         const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
         const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
@@ -323,11 +404,21 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_md_fwd_col(DView R, u64 *T2,
     const int c0 = blockIdx.x * 32;
     u64 x[8];
     const bool need_reduce = t.mod[a].p >= m.p4;   // else r' + q_j - hm < 8 q_j is already a valid lazy input
+    const FpConst f = t.fp[j];
     pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         u64 v = in[col_coarse_idx<LOGN>(c0, e)];
         x[e] = need_reduce ? submod(reduce64(v, m), hm, m.p) : v + m.p - hm;
+    }
+    if (f.ok != 0.0) {   // x < 5 q_j: exact as doubles
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+        fwd_col_pass_fp<LOGN>(xd, t.twfd + (size_t)j * G::N, f, as_fp(smem));
+#pragma unroll
+        for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = fp_bits(xd[e]);
+        return;
     }
     fwd_col_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, smem);
 #pragma unroll
@@ -353,10 +444,20 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *T2, DV
     const u64 qi = t.inv[a * t.K + j], qis = t.invs[a * t.K + j];
     const int t0 = blockIdx.x * NTT_TILE;
     u64 x[8];
+    const FpConst f = t.fp[j];
     pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
-    fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, t0, smem);
+    if (f.ok != 0.0) {
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = bits_fp(x[e]);
+        fwd_row_pass_fp<LOGN>(xd, t.twfd + (size_t)j * G::N, f, t0, as_fp(smem));
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = fp_to_canonical(xd[e], f);
+    } else {
+        fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, t0, smem);
+    }
     const u64 *mi = minuend.data + b * minuend.bs + s * minuend.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
     u64 *out = dst.data + sl.entry * dst.bs + s * dst.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
     // all epilogue loads are issued before the first store (out may alias base, so the compiler

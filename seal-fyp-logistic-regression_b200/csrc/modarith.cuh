@@ -141,3 +141,54 @@ __device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, u64 w, u64 ws, const Mod
     X = lazy_sub(s, m.p4, (unsigned)m.p4hi);
     Y = shoup_lazy(d, w, ws, m.negp);
 }
+
+// ================================================================================================
+// FP64 butterflies for primes below 2^41.
+// On B200 a warp-wide IMAD.WIDE occupies the integer multiplier for 8 cycles and IMAD.HI for 4
+// (16 resp. 32 lanes/clk/SM, profiles/micro/pipe_rates.cu), while DFMA / DADD / DMUL run at 64
+// lanes/clk/SM on their own pipe.  For small primes the butterfly is therefore done on integer-valued
+// doubles: a modular product costs 7 FP64 operations, all exact:
+//     h = RN(w*y),  l = w*y - h (FMA, exact error term),  q = rint(h/p),  r = h - q*p (FMA, exact
+//     because |h - q p| < 1.01 p is representable),  t = r + l,   |t| < 2p.
+// Values are signed and lazily bounded (|x| < 2^51 keeps every quantity an exact integer): forward
+// butterflies add at most 2p per stage, inverse sums double per stage and are reduced once per pass.
+// Results are bit-identical to the integer path because only exact integer arithmetic is used.
+struct FpConst {
+    double p, pinv, ninv, w1ni, ok, pad;
+};
+__device__ __forceinline__ double fp_rint(double v) {   // round to nearest integer, |v| < 2^51
+    const double M = 6755399441055744.0;                 // 1.5 * 2^52
+    return __dadd_rn(__dadd_rn(v, M), -M);
+}
+__device__ __forceinline__ double fp_mulmod(double y, double w, const FpConst &f) {
+    double h = __dmul_rn(w, y);
+    double l = __fma_rn(w, y, -h);
+    double q = fp_rint(__dmul_rn(h, f.pinv));
+    double r = __fma_rn(-q, f.p, h);
+    return __dadd_rn(r, l);
+}
+// x -> representative in about (-p/2, p/2)
+__device__ __forceinline__ double fp_reduce(double x, const FpConst &f) {
+    double q = fp_rint(__dmul_rn(x, f.pinv));
+    return __fma_rn(-q, f.p, x);
+}
+// exact conversions for integers below 2^52
+__device__ __forceinline__ double fp_from_u64(u64 v) {
+    return __dadd_rn(__longlong_as_double((long long)(v | 0x4330000000000000ull)), -4503599627370496.0);
+}
+__device__ __forceinline__ u64 fp_to_canonical(double x, const FpConst &f) {   // -> [0,p)
+    double v = fp_reduce(x, f);
+    if (v < 0.0) v = __dadd_rn(v, f.p);
+    return (u64)__double_as_longlong(__dadd_rn(v, 4503599627370496.0)) & 0x000fffffffffffffull;
+}
+__device__ __forceinline__ void ct_bfly_fp(double &X, double &Y, double w, const FpConst &f) {
+    double t = fp_mulmod(Y, w, f);
+    Y = __dadd_rn(X, -t);
+    X = __dadd_rn(X, t);
+}
+__device__ __forceinline__ void gs_bfly_fp(double &X, double &Y, double w, const FpConst &f) {
+    double s = __dadd_rn(X, Y);
+    double d = __dadd_rn(X, -Y);
+    X = s;
+    Y = fp_mulmod(d, w, f);
+}

@@ -231,3 +231,140 @@ __device__ __forceinline__ void inv_row_pass(u64 (&x)[8], const tw_t *__restrict
     for (int e = 0; e < 8; e++) x[e] = smem[sw(row_strided_li<LOGN>(e))];
     inv8<0>(x, ta, m);
 }
+
+// ================================================================================================
+// FP64 versions of the same passes (primes below 2^41, see modarith.cuh).  Twiddles are plain
+// doubles (8 bytes per node).  Shared memory holds the doubles' bit patterns.
+struct Tw8d {
+    double w[7];
+};
+template <int SKIP>
+__device__ __forceinline__ void load_tw8d(Tw8d &t, const double *__restrict__ tw, unsigned nd) {
+    if (SKIP < 1) t.w[0] = __ldg(tw + nd);
+    if (SKIP < 2) {
+        t.w[1] = __ldg(tw + 2 * nd);
+        t.w[2] = __ldg(tw + 2 * nd + 1);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) t.w[3 + q] = __ldg(tw + 4 * nd + q);
+}
+template <int SKIP>
+__device__ __forceinline__ void fwd8d(double (&x)[8], const Tw8d &t, const FpConst &f) {
+    if (SKIP < 1) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) ct_bfly_fp(x[e], x[e + 4], t.w[0], f);
+    }
+    if (SKIP < 2) {
+        ct_bfly_fp(x[0], x[2], t.w[1], f);
+        ct_bfly_fp(x[1], x[3], t.w[1], f);
+        ct_bfly_fp(x[4], x[6], t.w[2], f);
+        ct_bfly_fp(x[5], x[7], t.w[2], f);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) ct_bfly_fp(x[2 * q], x[2 * q + 1], t.w[3 + q], f);
+}
+template <int SKIP>
+__device__ __forceinline__ void inv8d(double (&x)[8], const Tw8d &t, const FpConst &f) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) gs_bfly_fp(x[2 * q], x[2 * q + 1], t.w[3 + q], f);
+    if (SKIP < 2) {
+        gs_bfly_fp(x[0], x[2], t.w[1], f);
+        gs_bfly_fp(x[1], x[3], t.w[1], f);
+        gs_bfly_fp(x[4], x[6], t.w[2], f);
+        gs_bfly_fp(x[5], x[7], t.w[2], f);
+    }
+    if (SKIP < 1) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) gs_bfly_fp(x[e], x[e + 4], t.w[0], f);
+    }
+}
+
+// forward column pass: |x| grows by at most 2p per stage (12p over the pass)
+template <int LOGN>
+__device__ __forceinline__ void fwd_col_pass_fp(double (&x)[8], const double *__restrict__ tw, const FpConst &f, double *smem) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Tw8d t1, t2;
+    load_tw8d<0>(t1, tw, 1u);
+    load_tw8d<0>(t2, tw, 8u + k);
+    fwd8d<0>(x, t1, f);
+#pragma unroll
+    for (int e = 0; e < 8; e++) smem[(k + 8 * e) * 32 + lane] = x[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = smem[(8 * k + e) * 32 + lane];
+    fwd8d<0>(x, t2, f);
+}
+// inverse column pass: inputs reduced (|x| < p), returns values scaled by N^-1 with |x| < 2p
+template <int LOGN>
+__device__ __forceinline__ void inv_col_pass_fp(double (&x)[8], const double *__restrict__ twi, const FpConst &f, double *smem) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Tw8d t1, t2;
+    load_tw8d<0>(t1, twi, 8u + k);
+    load_tw8d<1>(t2, twi, 1u);
+    inv8d<0>(x, t1, f);
+#pragma unroll
+    for (int e = 0; e < 8; e++) smem[(8 * k + e) * 32 + lane] = x[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = smem[(k + 8 * e) * 32 + lane];
+    inv8d<1>(x, t2, f);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        double s = __dadd_rn(x[e], x[e + 4]);
+        double d = __dadd_rn(x[e], -x[e + 4]);
+        x[e] = fp_mulmod(s, f.ninv, f);
+        x[e + 4] = fp_mulmod(d, f.w1ni, f);
+    }
+}
+// forward row pass: strided-side in, contiguous-side out
+template <int LOGN>
+__device__ __forceinline__ void fwd_row_pass_fp(double (&x)[8], const double *__restrict__ tw, const FpConst &f, int t0, double *smem) {
+    typedef NttGeo<LOGN> G;
+    constexpr int SK3 = 3 - (G::REM > 0 ? G::REM : 3);
+    Tw8d ta, tb;
+    load_tw8d<0>(ta, tw, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)));
+    load_tw8d<0>(tb, tw, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)));
+    fwd8d<0>(x, ta, f);
+#pragma unroll
+    for (int e = 0; e < 8; e++) smem[sw(row_strided_li<LOGN>(e))] = x[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = smem[sw(row_mid_li<LOGN>(e))];
+    fwd8d<0>(x, tb, f);
+    if (G::REM > 0) {
+        load_tw8d<SK3>(ta, tw, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3));
+#pragma unroll
+        for (int e = 0; e < 8; e++) smem[sw(row_mid_li<LOGN>(e))] = x[e];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = smem[sw(row_contig_li(e))];
+        fwd8d<SK3>(x, ta, f);
+    }
+}
+// inverse row pass: contiguous-side in (|x| <= p), strided-side out, reduced to |x| < p at the end
+template <int LOGN>
+__device__ __forceinline__ void inv_row_pass_fp(double (&x)[8], const double *__restrict__ twi, const FpConst &f, int t0, double *smem) {
+    typedef NttGeo<LOGN> G;
+    constexpr int SK3 = 3 - (G::REM > 0 ? G::REM : 3);
+    Tw8d ta, tb;
+    load_tw8d<0>(tb, twi, 512u + ((unsigned)(t0 + row_mid_li<LOGN>(0)) >> (LOGN - 9)));
+    if (G::REM > 0) {
+        load_tw8d<SK3>(ta, twi, (1u << (LOGN - 3)) + ((unsigned)(t0 + row_contig_li(0)) >> 3));
+        inv8d<SK3>(x, ta, f);
+#pragma unroll
+        for (int e = 0; e < 8; e++) smem[sw(row_contig_li(e))] = x[e];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = smem[sw(row_mid_li<LOGN>(e))];
+    }
+    inv8d<0>(x, tb, f);
+    load_tw8d<0>(ta, twi, 64u + ((unsigned)(t0 + row_strided_li<LOGN>(0)) >> (LOGN - 6)));
+#pragma unroll
+    for (int e = 0; e < 8; e++) smem[sw(row_mid_li<LOGN>(e))] = x[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = smem[sw(row_strided_li<LOGN>(e))];
+    inv8d<0>(x, ta, f);
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = fp_reduce(x[e], f);   // sums doubled 9 times: bring back below p
+}

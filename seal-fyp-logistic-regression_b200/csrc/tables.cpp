@@ -84,6 +84,9 @@ void build_tables(int log_n, const std::vector<uint64_t> &primes, HostTables &ou
     out.inv.assign(K * K, 0);
     out.invs.assign(K * K, 0);
     out.halfmod.assign(K * K, 0);
+    out.fpc.assign(K * 6, 0.0);
+    out.twfd.assign(K * n, 0.0);
+    out.twid.assign(K * n, 0.0);
     for (size_t j = 0; j < K; ++j) {
         const uint64_t p = primes[j];
         if ((p >> 60) != 0 || !is_prime_u64(p) || (p - 1) % (2 * n) != 0)
@@ -119,6 +122,18 @@ void build_tables(int log_n, const std::vector<uint64_t> &primes, HostTables &ou
         m[9] = 4 * p;
         m[10] = 0 - p;
         m[11] = (4 * p) >> 32;
+        if ((p >> 41) == 0) {   // small prime: exact FP64 butterflies are possible (|values| < 2^51)
+            double *f = &out.fpc[j * 6];
+            f[0] = (double)p;
+            f[1] = 1.0 / (double)p;
+            f[2] = (double)n_inv;
+            f[3] = (double)m[6];
+            f[4] = 1.0;
+            for (size_t node = 0; node < n; ++node) {
+                out.twfd[j * n + node] = (double)tf[2 * node];
+                out.twid[j * n + node] = (double)ti[2 * node];
+            }
+        }
     }
     for (size_t a = 0; a < K; ++a)
         for (size_t j = 0; j < K; ++j) {
