@@ -467,6 +467,13 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
     u64 *ACC = T1 + (size_t)Bc * L * (L + 1) * N;
     u64 *T2 = ACC + (size_t)Bc * 2 * (L + 1) * N;
     rt.tgt_poly = mode == 1 ? 2 : 1;
+    // output limbs by prime size: integer kernel for large primes, FP64 kernel for small ones
+    JjList big{}, small{};
+    for (int jj = 0; jj <= L; jj++) {
+        const int pj = jj == L ? K - 1 : jj;
+        JjList &dst = (c->primes[pj] >> 41) == 0 ? small : big;
+        dst.jj[dst.n++] = (signed char)jj;
+    }
     for (int b0 = 0; b0 < nslots; b0 += Bc) {
         const int bc = (nslots - b0) < Bc ? (nslots - b0) : Bc;
         rt.b0 = b0;
@@ -486,9 +493,16 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         LAUNCH_CHECK(c);                                                                                                \
         launch_pdl(k_ks_modup_col<LN>, dim3(G::COL_TILES, L *(L + 1), bc), st, D, T1, L, c->t);                 \
         LAUNCH_CHECK(c);                                                                                                \
-        if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, L + 1, bc), st, T1, rt, ACC, L, c->t); \
-        else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, L + 1, bc), st, T1, rt, ACC, L, c->t);          \
-        LAUNCH_CHECK(c);                                                                                                \
+        if (big.n) {                                                                                                    \
+            if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, c->t); \
+            else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, c->t);         \
+            LAUNCH_CHECK(c);                                                                                            \
+        }                                                                                                               \
+        if (small.n) {                                                                                                  \
+            if (mode == 2) launch_pdl(k_ks_mac_fp<LN, true>, dim3(G::ROW_TILES, small.n, bc), st, T1, rt, ACC, L, small, c->t); \
+            else launch_pdl(k_ks_mac_fp<LN, false>, dim3(G::ROW_TILES, small.n, bc), st, T1, rt, ACC, L, small, c->t);  \
+            LAUNCH_CHECK(c);                                                                                            \
+        }                                                                                                               \
         launch_pdl(k_inv_row<LN>, dim3(G::ROW_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);               \
         LAUNCH_CHECK(c);                                                                                                \
         launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);         \

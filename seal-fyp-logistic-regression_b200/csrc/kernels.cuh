@@ -313,12 +313,18 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *D, u
 // (4) mod-up row pass fused with the key inner product: for output limb jj of ciphertext b,
 //     acc_k = sum_i NTT_pj(digit_i) (.) ksk[i][k][pj]     (k = 0,1), 128-bit lazy sums,
 // one Barrett reduction at the end.  Key limbs stream once from HBM, fully coalesced.
+// The output limbs are split by prime size into two launches (JjList): large primes take the
+// integer path below, small primes the FP64 kernel k_ks_mac_fp.
+struct JjList {
+    int n;
+    signed char jj[36];
+};
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRoute rt, u64 *ACC, int L, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     pdl_launch_dependents();
-    const int jj = blockIdx.y, b = blockIdx.z;
+    const int jj = list.jj[blockIdx.y], b = blockIdx.z;
     const KsSel sl = route_sel(rt, b);
     const DView tgt = rt.v[sl.src];
     const uint32_t *__restrict__ perm = GALOIS ? route_perm(rt, sl) : nullptr;
@@ -326,7 +332,6 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
     const int K = t.K, pj = jj == L ? K - 1 : jj;
     const ModConst m = load_mod(t, pj);
     const tw_t *tw = t.twf + (size_t)pj * G::N;
-    const FpConst f = t.fp[pj];
     const int t0 = blockIdx.x * NTT_TILE;
     u64 lo0[8], hi0[8], lo1[8], hi1[8];
 #pragma unroll
@@ -352,16 +357,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
 #pragma unroll
             for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
             __syncthreads();  // previous iteration's shared-memory reads are done
-            if (f.ok != 0.0) {
-                double xd[8];
-#pragma unroll
-                for (int e = 0; e < 8; e++) xd[e] = bits_fp(x[e]);
-                fwd_row_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, t0, as_fp(smem));
-#pragma unroll
-                for (int e = 0; e < 8; e++) x[e] = fp_to_canonical(xd[e], f);
-            } else {
-                fwd_row_pass<LOGN>(x, tw, m, t0, smem);
-            }
+            fwd_row_pass<LOGN>(x, tw, m, t0, smem);
         }
         const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
         const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
@@ -386,6 +382,71 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
         reinterpret_cast<ulonglong2 *>(o0)[v] = r0;
         reinterpret_cast<ulonglong2 *>(o1)[v] = r1;
     }
+}
+
+// FP64 variant for output limbs with a small prime: transform, products and the running sums all
+// stay on the FP64 pipe (|sum| < 2p per term, at most 32 terms: exact), one canonicalisation at the end
+template <int LOGN, bool GALOIS>
+__global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    pdl_launch_dependents();
+    const int jj = list.jj[blockIdx.y], b = blockIdx.z;
+    const KsSel sl = route_sel(rt, b);
+    const DView tgt = rt.v[sl.src];
+    const uint32_t *__restrict__ perm = GALOIS ? route_perm(rt, sl) : nullptr;
+    const u64 *__restrict__ ksk = route_key(rt, sl);
+    const int K = t.K, pj = jj == L ? K - 1 : jj;
+    const FpConst f = t.fp[pj];
+    const double *tw = t.twfd + (size_t)pj * G::N;
+    const int t0 = blockIdx.x * NTT_TILE;
+    double a0[8], a1[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) a0[e] = a1[e] = 0.0;
+    pdl_wait();
+    for (int i = 0; i < L; i++) {
+        double x[8];
+        prefetch_l2(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+        prefetch_l2(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+        if (i == pj) {
+            const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
+            u64 xi[8];
+            if (GALOIS) {
+                unsigned ix[8];
+                load_perm8(ix, perm + t0 + 8 * threadIdx.x);
+#pragma unroll
+                for (int e = 0; e < 8; e++) xi[e] = in[ix[e]];
+            } else {
+                load8(xi, in + t0 + 8 * threadIdx.x);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = fp_from_u64(xi[e]);
+        } else {
+            const u64 *in = T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N;
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = bits_fp(in[t0 + row_strided_li<LOGN>(e)]);
+            __syncthreads();
+            fwd_row_pass_fp<LOGN>(x, tw, f, t0, as_fp(smem));   // lazy, |x| < 32p
+        }
+        const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+        const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            ulonglong2 a = __ldg(k0 + v), c = __ldg(k1 + v);
+            a0[2 * v] = __dadd_rn(a0[2 * v], fp_mulmod(x[2 * v], fp_from_u64(a.x), f));
+            a0[2 * v + 1] = __dadd_rn(a0[2 * v + 1], fp_mulmod(x[2 * v + 1], fp_from_u64(a.y), f));
+            a1[2 * v] = __dadd_rn(a1[2 * v], fp_mulmod(x[2 * v], fp_from_u64(c.x), f));
+            a1[2 * v + 1] = __dadd_rn(a1[2 * v + 1], fp_mulmod(x[2 * v + 1], fp_from_u64(c.y), f));
+        }
+    }
+    u64 r0[8], r1[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        r0[e] = fp_to_canonical(a0[e], f);
+        r1[e] = fp_to_canonical(a1[e], f);
+    }
+    store8(ACC + (((u64)b * 2 + 0) * (L + 1) + jj) * G::N + t0 + 8 * threadIdx.x, r0);
+    store8(ACC + (((u64)b * 2 + 1) * (L + 1) + jj) * G::N + t0 + 8 * threadIdx.x, r1);
 }
 
 // (7) mod-down / rescale, column pass: R holds r' = (INTT(last limb) + half) mod q_a for poly
