@@ -509,13 +509,12 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *T2, DV
     pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
-    if (f.ok != 0.0) {
-        double xd[8];
+    double xd[8];
+    const bool fp = f.ok != 0.0;
+    if (fp) {
 #pragma unroll
         for (int e = 0; e < 8; e++) xd[e] = bits_fp(x[e]);
-        fwd_row_pass_fp<LOGN>(xd, t.twfd + (size_t)j * G::N, f, t0, as_fp(smem));
-#pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = fp_to_canonical(xd[e], f);
+        fwd_row_pass_fp<LOGN>(xd, t.twfd + (size_t)j * G::N, f, t0, as_fp(smem));   // lazy, |xd| < 32p
     } else {
         fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, t0, smem);
     }
@@ -540,12 +539,22 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *T2, DV
     // (< 8p + 2^32) is subtracted from minuend + 9p (a multiple of p, no underflow), one truncated
     // Shoup multiply brings the product to [0,4p), two conditional subtractions make it canonical
     const u64 p9 = m.p4 + m.p4 + m.p;
+    if (fp) {   // small prime: the whole epilogue on the FP64 pipe
+        const double qd = fp_from_u64(qi);
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        u64 r = shoup_lazy(mv[e] + p9 - x[e], qi, qis, m.negp);
-        r = csub(csub(r, m.p2), m.p);
-        if (MODE == 1 || (MODE == 2 && s == 0)) r = addmod(r, bv[e], m.p);
-        x[e] = r;
+        for (int e = 0; e < 8; e++) {
+            double r = fp_mulmod(__dadd_rn(fp_from_u64(mv[e]), -xd[e]), qd, f);
+            if (MODE == 1 || (MODE == 2 && s == 0)) r = __dadd_rn(r, fp_from_u64(bv[e]));
+            x[e] = fp_to_canonical(r, f);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            u64 r = shoup_lazy(mv[e] + p9 - x[e], qi, qis, m.negp);
+            r = csub(csub(r, m.p2), m.p);
+            if (MODE == 1 || (MODE == 2 && s == 0)) r = addmod(r, bv[e], m.p);
+            x[e] = r;
+        }
     }
     store8(out, x);
     if (MODE == 2 && rt.has_acc) {
