@@ -70,6 +70,9 @@ struct ckks_ctx {
     // rotate-and-sum chains: private stream + cached CUDA graphs of two ping-pong steps
     cudaStream_t chain_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    // side stream: the FP64 inner-product kernel (small-prime limbs) runs beside the integer one
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     struct ChainGraph {
         cudaGraphExec_t exec;
         uint64_t launches;
@@ -166,6 +169,9 @@ extern "C" void ckks_ctx_destroy(ckks_ctx *c) {
     for (auto &kv : c->perms) cudaFree(kv.second);
     for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
     if (c->chain_stream) cudaStreamDestroy(c->chain_stream);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     cudaFree(c->d_mod); cudaFree(c->d_twf); cudaFree(c->d_twi);
@@ -467,6 +473,11 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
     u64 *ACC = T1 + (size_t)Bc * L * (L + 1) * N;
     u64 *T2 = ACC + (size_t)Bc * 2 * (L + 1) * N;
     rt.tgt_poly = mode == 1 ? 2 : 1;
+    if (!c->side_stream) {
+        CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
     // output limbs by prime size: integer kernel for large primes, FP64 kernel for small ones
     JjList big{}, small{};
     for (int jj = 0; jj <= L; jj++) {
@@ -493,14 +504,22 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         LAUNCH_CHECK(c);                                                                                                \
         launch_pdl(k_ks_modup_col<LN>, dim3(G::COL_TILES, L *(L + 1), bc), st, D, T1, L, c->t);                 \
         LAUNCH_CHECK(c);                                                                                                \
+        /* the FP64 inner product (small-prime limbs) is independent of the integer one and of the special-prime  \
+           INTT that follows: fork it onto the side stream, join before the last kernel reads its output */       \
+        cudaStream_t sfp = (big.n && small.n) ? c->side_stream : st;                                                    \
+        if (small.n) {                                                                                                  \
+            if (sfp != st) {                                                                                            \
+                CU(cudaEventRecord(c->ev_fork, st));                                                                    \
+                CU(cudaStreamWaitEvent(sfp, c->ev_fork, 0));                                                            \
+            }                                                                                                           \
+            if (mode == 2) k_ks_mac_fp<LN, true><<<dim3(G::ROW_TILES, small.n, bc), NTT_THREADS, 0, sfp>>>(T1, rt, ACC, L, small, c->t); \
+            else k_ks_mac_fp<LN, false><<<dim3(G::ROW_TILES, small.n, bc), NTT_THREADS, 0, sfp>>>(T1, rt, ACC, L, small, c->t); \
+            LAUNCH_CHECK(c);                                                                                            \
+            if (sfp != st) CU(cudaEventRecord(c->ev_join, sfp));                                                        \
+        }                                                                                                               \
         if (big.n) {                                                                                                    \
             if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, c->t); \
             else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, c->t);         \
-            LAUNCH_CHECK(c);                                                                                            \
-        }                                                                                                               \
-        if (small.n) {                                                                                                  \
-            if (mode == 2) launch_pdl(k_ks_mac_fp<LN, true>, dim3(G::ROW_TILES, small.n, bc), st, T1, rt, ACC, L, small, c->t); \
-            else launch_pdl(k_ks_mac_fp<LN, false>, dim3(G::ROW_TILES, small.n, bc), st, T1, rt, ACC, L, small, c->t);  \
             LAUNCH_CHECK(c);                                                                                            \
         }                                                                                                               \
         launch_pdl(k_inv_row<LN>, dim3(G::ROW_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);               \
@@ -509,6 +528,7 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         LAUNCH_CHECK(c);                                                                                                \
         launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, L, 2 * bc), st, spec, T2, L, K - 1, c->t);              \
         LAUNCH_CHECK(c);                                                                                                \
+        if (sfp != st) CU(cudaStreamWaitEvent(st, c->ev_join, 0));                                                      \
         if (mode == 2) launch_pdl(k_md_fwd_row<LN, 2>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
         else launch_pdl(k_md_fwd_row<LN, 1>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
         LAUNCH_CHECK(c);                                                                                                \
