@@ -404,7 +404,7 @@ def run_gpu(args):
         traffic = json.load(open(tpath)).get("bytes_per_launch_group")
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "binding_resource": "integer multiply pipe (fmaheavy 48-70% busy per kernel, ncu) -- see DESIGN.md section 4",
+        "binding_resource": "integer multiplier (IMAD.WIDE 16 lanes/clk/SM) for the 60-bit primes, FP64 pipe for the 40-bit primes -- see DESIGN.md section 4",
         "kernel": "Galois key switch pipeline (k_ks_intt_row, k_inv_col, k_ks_modup_col, k_ks_mac, k_inv_row, "
                   "k_inv_col, k_md_fwd_col, k_md_fwd_row), batch %d, N=32768, L=%d" % (nb, Lk),
         "algorithmic_bytes_per_launch_group": alg, "ms_per_launch_group": ks_ms, "peak_source": peak_src,
