@@ -303,6 +303,8 @@ def run_gpu(args):
     R_total = R_PER_GPU * world
 
     ctx.reserve(M * C_FEAT, ctx.top_limbs)
+    if os.environ.get("CKKS_CHAIN_LANES"):
+        ctx.set_chain_lanes(int(os.environ["CKKS_CHAIN_LANES"]))
 
     def epoch(cols, labs, wb, wct):
         grad = lr.column_epoch_gradient(ev, cols, labs, wb, C_FEAT, B_MINI, SCALE, keys, enc, encr,

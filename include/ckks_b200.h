@@ -68,6 +68,8 @@ uint64_t ckks_ctx_prime(const ckks_ctx *ctx, int j);
 int ckks_ctx_set_rounding(ckks_ctx *ctx, int round_half);
 /* cap (bytes) on the internal key-switch workspace; larger batches are processed in chunks */
 int ckks_ctx_set_workspace_cap(ckks_ctx *ctx, size_t bytes);
+/* number of concurrent half-/quarter-batch pipelines a rotate-and-sum chain is split into (1..4, default 2) */
+int ckks_ctx_set_chain_lanes(ckks_ctx *ctx, int lanes);
 /* pre-allocate the workspace for key switching `batch` ciphertexts at `limbs` (needed before
  * CUDA-graph capture, which forbids allocation) */
 int ckks_ctx_reserve(ckks_ctx *ctx, int batch, int limbs);

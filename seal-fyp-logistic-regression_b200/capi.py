@@ -44,6 +44,7 @@ SIGNATURES = {
     "ckks_ctx_prime": (C.c_uint64, [C.c_void_p, C.c_int]),
     "ckks_ctx_set_rounding": (C.c_int, [C.c_void_p, C.c_int]),
     "ckks_ctx_set_workspace_cap": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "ckks_ctx_set_chain_lanes": (C.c_int, [C.c_void_p, C.c_int]),
     "ckks_ctx_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ckks_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
     "ckks_ctx_reset_launch_count": (None, [C.c_void_p]),

@@ -70,9 +70,16 @@ struct ckks_ctx {
     // rotate-and-sum chains: private stream + cached CUDA graphs of two ping-pong steps
     cudaStream_t chain_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-    // side stream: the FP64 inner-product kernel (small-prime limbs) runs beside the integer one
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // lane 0 is the normal path; lane 1 has its own workspace, side stream and events so that a chain can
+    // run two half-batches as concurrent pipelines (each lane's FP64 inner-product kernel runs on its side
+    // stream beside the integer one)
+    struct Lane {
+        u64 *ws = nullptr;
+        size_t ws_bytes = 0;
+        cudaStream_t side = nullptr, main = nullptr;
+        cudaEvent_t fork = nullptr, join = nullptr, begin = nullptr, end = nullptr;
+    } lane[4];
+    int chain_lanes = 2;
     struct ChainGraph {
         cudaGraphExec_t exec;
         uint64_t launches;
@@ -169,9 +176,13 @@ extern "C" void ckks_ctx_destroy(ckks_ctx *c) {
     for (auto &kv : c->perms) cudaFree(kv.second);
     for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
     if (c->chain_stream) cudaStreamDestroy(c->chain_stream);
-    if (c->side_stream) cudaStreamDestroy(c->side_stream);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (auto &ln : c->lane) {
+        if (ln.side) cudaStreamDestroy(ln.side);
+        if (ln.main) cudaStreamDestroy(ln.main);
+        for (cudaEvent_t e : {ln.fork, ln.join, ln.begin, ln.end})
+            if (e) cudaEventDestroy(e);
+        if (&ln != &c->lane[0]) cudaFree(ln.ws);
+    }
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     cudaFree(c->d_mod); cudaFree(c->d_twf); cudaFree(c->d_twi);
@@ -186,6 +197,11 @@ extern "C" int ckks_ctx_n_primes(const ckks_ctx *c) { return c->K; }
 extern "C" uint64_t ckks_ctx_prime(const ckks_ctx *c, int j) { return (j >= 0 && j < c->K) ? c->primes[j] : 0; }
 extern "C" int ckks_ctx_set_rounding(ckks_ctx *c, int r) {
     c->t.round_half = r ? 1 : 0;
+    return CKKS_OK;
+}
+extern "C" int ckks_ctx_set_chain_lanes(ckks_ctx *c, int lanes) {
+    if (lanes < 1 || lanes > 4) return fail(CKKS_ERR_INVALID, "chain lanes must be 1..4");
+    c->chain_lanes = lanes;
     return CKKS_OK;
 }
 extern "C" int ckks_ctx_set_workspace_cap(ckks_ctx *c, size_t bytes) {
@@ -207,6 +223,31 @@ static int ensure_ws(ckks_ctx *c, size_t bytes) {
     cudaError_t e = cudaMalloc((void **)&c->ws, bytes);
     if (e != cudaSuccess) return fail(CKKS_ERR_NOMEM, "workspace allocation failed");
     c->ws_bytes = bytes;
+    return CKKS_OK;
+}
+
+static int ensure_lane(ckks_ctx *c, int li, size_t bytes) {
+    ckks_ctx::Lane &ln = c->lane[li];
+    if (!ln.side) {
+        CU(cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
+        for (cudaEvent_t *e : {&ln.fork, &ln.join, &ln.begin, &ln.end}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    if (li == 0) {
+        int rc = ensure_ws(c, bytes);
+        ln.ws = c->ws;
+        ln.ws_bytes = c->ws_bytes;
+        return rc;
+    }
+    if (bytes <= ln.ws_bytes) return CKKS_OK;
+    if (ln.ws) {
+        CU(cudaDeviceSynchronize());
+        CU(cudaFree(ln.ws));
+        ln.ws = nullptr;
+        ln.ws_bytes = 0;
+    }
+    if (cudaMalloc((void **)&ln.ws, bytes) != cudaSuccess) return fail(CKKS_ERR_NOMEM, "workspace allocation failed");
+    ln.ws_bytes = bytes;
     return CKKS_OK;
 }
 
@@ -462,22 +503,18 @@ static int get_perm(ckks_ctx *c, uint64_t g, const uint32_t **out) {
 // Batched key switch over `nslots` launch slots.
 // mode 1: relinearize (target = poly 2 of the source, base = polys 0,1)
 // mode 2: Galois      (target = permuted poly 1, base = permuted poly 0)
-static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaStream_t st, bool chained = false) {
+static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaStream_t st, bool chained = false, int li = 0) {
     const int K = c->K;
     const size_t N = c->n;
     const int Bc = ks_chunk(c, nslots, L);
     int rc;
-    if ((rc = ensure_ws(c, ks_words_per_ct(c, L) * 8 * (size_t)Bc))) return rc;
-    u64 *D = c->ws;
+    if ((rc = ensure_lane(c, li, ks_words_per_ct(c, L) * 8 * (size_t)Bc))) return rc;
+    ckks_ctx::Lane &ln = c->lane[li];
+    u64 *D = ln.ws;
     u64 *T1 = D + (size_t)Bc * L * N;
     u64 *ACC = T1 + (size_t)Bc * L * (L + 1) * N;
     u64 *T2 = ACC + (size_t)Bc * 2 * (L + 1) * N;
     rt.tgt_poly = mode == 1 ? 2 : 1;
-    if (!c->side_stream) {
-        CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    }
     // output limbs by prime size: integer kernel for large primes, FP64 kernel for small ones
     JjList big{}, small{};
     for (int jj = 0; jj <= L; jj++) {
@@ -506,16 +543,16 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         LAUNCH_CHECK(c);                                                                                                \
         /* the FP64 inner product (small-prime limbs) is independent of the integer one and of the special-prime  \
            INTT that follows: fork it onto the side stream, join before the last kernel reads its output */       \
-        cudaStream_t sfp = (big.n && small.n) ? c->side_stream : st;                                                    \
+        cudaStream_t sfp = (big.n && small.n) ? ln.side : st;                                                          \
         if (small.n) {                                                                                                  \
             if (sfp != st) {                                                                                            \
-                CU(cudaEventRecord(c->ev_fork, st));                                                                    \
-                CU(cudaStreamWaitEvent(sfp, c->ev_fork, 0));                                                            \
+                CU(cudaEventRecord(ln.fork, st));                                                                       \
+                CU(cudaStreamWaitEvent(sfp, ln.fork, 0));                                                               \
             }                                                                                                           \
             if (mode == 2) k_ks_mac_fp<LN, true><<<dim3(G::ROW_TILES, small.n, bc), NTT_THREADS, 0, sfp>>>(T1, rt, ACC, L, small, c->t); \
             else k_ks_mac_fp<LN, false><<<dim3(G::ROW_TILES, small.n, bc), NTT_THREADS, 0, sfp>>>(T1, rt, ACC, L, small, c->t); \
             LAUNCH_CHECK(c);                                                                                            \
-            if (sfp != st) CU(cudaEventRecord(c->ev_join, sfp));                                                        \
+            if (sfp != st) CU(cudaEventRecord(ln.join, sfp));                                                           \
         }                                                                                                               \
         if (big.n) {                                                                                                    \
             if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, c->t); \
@@ -528,7 +565,7 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         LAUNCH_CHECK(c);                                                                                                \
         launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, L, 2 * bc), st, spec, T2, L, K - 1, c->t);              \
         LAUNCH_CHECK(c);                                                                                                \
-        if (sfp != st) CU(cudaStreamWaitEvent(st, c->ev_join, 0));                                                      \
+        if (sfp != st) CU(cudaStreamWaitEvent(st, ln.join, 0));                                                         \
         if (mode == 2) launch_pdl(k_md_fwd_row<LN, 2>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
         else launch_pdl(k_md_fwd_row<LN, 1>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
         LAUNCH_CHECK(c);                                                                                                \
@@ -669,57 +706,81 @@ extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const c
     const int L = a->limbs, B = a->batch;
     if ((rc = ensure_ws(c, ks_words_per_ct(c, L) * 8 * (size_t)ks_chunk(c, B, L)))) return rc;
     cudaStream_t user = (cudaStream_t)s;
-    auto one = [&](const ckks_view *src, const ckks_view *dst, cudaStream_t st, bool chained) -> int {
-        KsRoute rt = uniform_route(src, dst, perm, it->second);
-        rt.accv = dv(acc);
+    // one step on the batch entries [off, off+cnt) through lane `li`
+    auto one = [&](const ckks_view *src, const ckks_view *dst, cudaStream_t st, bool chained, int li, int off, int cnt) -> int {
+        ckks_view vs = *src, vd = *dst, va = *acc;
+        vs.data += (uint64_t)off * vs.batch_stride;
+        vd.data += (uint64_t)off * vd.batch_stride;
+        va.data += (uint64_t)off * va.batch_stride;
+        vs.batch = vd.batch = va.batch = cnt;
+        KsRoute rt = uniform_route(&vs, &vd, perm, it->second);
+        rt.accv = dv(&va);
         rt.has_acc = 1;
-        return keyswitch(c, 2, L, B, rt, st, chained);
+        return keyswitch(c, 2, L, cnt, rt, st, chained, li);
     };
     int done = 0;
     if (count >= 4) {
-        if (!c->chain_stream) {
-            CU(cudaStreamCreateWithFlags(&c->chain_stream, cudaStreamNonBlocking));
+        // two half-batches run as independent pipelines (lanes) on their own streams: the short kernels of
+        // one lane (special-prime INTT: 1-2 waves) overlap the long ones of the other.  Each lane replays a
+        // cached CUDA graph of two ping-pong steps; the lanes only meet again at the end of the chain.
+        int nl = c->chain_lanes;
+        while (nl > 1 && B / nl < 8) nl--;
+        int split[5];
+        for (int li = 0; li <= nl; li++) split[li] = (int)((long)B * li / nl);
+        if (!c->ev_in) {
             CU(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
         }
-        std::vector<uint64_t> key = {(uint64_t)a->data, (uint64_t)b->data, (uint64_t)acc->data, (uint64_t)it->second, g,
-                                     (uint64_t)L, (uint64_t)B, a->batch_stride, a->poly_stride, b->batch_stride, b->poly_stride,
-                                     acc->batch_stride, acc->poly_stride, (uint64_t)c->ws, (uint64_t)c->t.round_half};
-        auto gi = c->chain_graphs.find(key);
-        if (gi == c->chain_graphs.end()) {
-            cudaGraph_t graph = nullptr;
-            uint64_t before = c->launches;
-            CU(cudaStreamBeginCapture(c->chain_stream, cudaStreamCaptureModeThreadLocal));
-            rc = one(a, b, c->chain_stream, false);
-            if (!rc) rc = one(b, a, c->chain_stream, true);
-            cudaError_t ce = cudaStreamEndCapture(c->chain_stream, &graph);
-            uint64_t per = c->launches - before;
-            c->launches = before;
-            if (rc) return rc;
-            if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
-            ckks_ctx::ChainGraph cg{};
-            cg.launches = per;
-            ce = cudaGraphInstantiate(&cg.exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
-            if (c->chain_graphs.size() > 64) {   // bounded cache
-                for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
-                c->chain_graphs.clear();
+        cudaGraphExec_t execs[4] = {nullptr, nullptr, nullptr, nullptr};
+        uint64_t per_pair = 0;
+        for (int li = 0; li < nl; li++) {
+            const int off = split[li], cnt = split[li + 1] - split[li];
+            if ((rc = ensure_lane(c, li, ks_words_per_ct(c, L) * 8 * (size_t)ks_chunk(c, cnt, L)))) return rc;
+            ckks_ctx::Lane &ln = c->lane[li];
+            std::vector<uint64_t> key = {(uint64_t)a->data, (uint64_t)b->data, (uint64_t)acc->data, (uint64_t)it->second, g,
+                                         (uint64_t)L, (uint64_t)off, (uint64_t)cnt, a->batch_stride, a->poly_stride, b->batch_stride,
+                                         b->poly_stride, acc->batch_stride, acc->poly_stride, (uint64_t)ln.ws, (uint64_t)c->t.round_half};
+            auto gi = c->chain_graphs.find(key);
+            if (gi == c->chain_graphs.end()) {
+                cudaGraph_t graph = nullptr;
+                uint64_t before = c->launches;
+                CU(cudaStreamBeginCapture(ln.main, cudaStreamCaptureModeThreadLocal));
+                rc = one(a, b, ln.main, false, li, off, cnt);
+                if (!rc) rc = one(b, a, ln.main, true, li, off, cnt);
+                cudaError_t ce = cudaStreamEndCapture(ln.main, &graph);
+                uint64_t per = c->launches - before;
+                c->launches = before;
+                if (rc) return rc;
+                if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+                ckks_ctx::ChainGraph cg{};
+                cg.launches = per;
+                ce = cudaGraphInstantiate(&cg.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+                if (c->chain_graphs.size() > 64) {   // bounded cache
+                    for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
+                    c->chain_graphs.clear();
+                }
+                gi = c->chain_graphs.emplace(key, cg).first;
             }
-            gi = c->chain_graphs.emplace(key, cg).first;
+            execs[li] = gi->second.exec;
+            per_pair += gi->second.launches;
         }
         CU(cudaEventRecord(c->ev_in, user));
-        CU(cudaStreamWaitEvent(c->chain_stream, c->ev_in, 0));
         const int pairs = count / 2;
-        for (int i = 0; i < pairs; i++) CU(cudaGraphLaunch(gi->second.exec, c->chain_stream));
-        c->launches += gi->second.launches * (uint64_t)pairs;
-        CU(cudaEventRecord(c->ev_out, c->chain_stream));
-        CU(cudaStreamWaitEvent(user, c->ev_out, 0));
+        for (int li = 0; li < nl; li++) CU(cudaStreamWaitEvent(c->lane[li].main, c->ev_in, 0));
+        for (int i = 0; i < pairs; i++)
+            for (int li = 0; li < nl; li++) CU(cudaGraphLaunch(execs[li], c->lane[li].main));
+        for (int li = 0; li < nl; li++) {
+            CU(cudaEventRecord(c->lane[li].end, c->lane[li].main));
+            CU(cudaStreamWaitEvent(user, c->lane[li].end, 0));
+        }
+        c->launches += per_pair * (uint64_t)pairs;
         done = pairs * 2;
     }
     const ckks_view *src = a, *dst = b;
     for (; done < count; done++) {
-        if ((rc = one(src, dst, user, false))) return rc;
+        if ((rc = one(src, dst, user, false, 0, 0, B))) return rc;
         const ckks_view *t = src;
         src = dst;
         dst = t;

@@ -67,6 +67,9 @@ class Context:
     def set_workspace_cap(self, nbytes):
         check(self.lib.ckks_ctx_set_workspace_cap(self._h, int(nbytes)))
 
+    def set_chain_lanes(self, lanes):
+        check(self.lib.ckks_ctx_set_chain_lanes(self._h, int(lanes)))
+
     def reserve(self, batch, limbs):
         check(self.lib.ckks_ctx_reserve(self._h, batch, limbs))
 
