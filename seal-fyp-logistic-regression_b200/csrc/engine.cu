@@ -503,7 +503,7 @@ static int get_perm(ckks_ctx *c, uint64_t g, const uint32_t **out) {
 // Batched key switch over `nslots` launch slots.
 // mode 1: relinearize (target = poly 2 of the source, base = polys 0,1)
 // mode 2: Galois      (target = permuted poly 1, base = permuted poly 0)
-static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaStream_t st, bool chained = false, int li = 0) {
+static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaStream_t st, bool chained = false, int li = 0, int slot0 = 0) {
     const int K = c->K;
     const size_t N = c->n;
     const int Bc = ks_chunk(c, nslots, L);
@@ -522,8 +522,8 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         JjList &dst = (c->primes[pj] >> 41) == 0 ? small : big;
         dst.jj[dst.n++] = (signed char)jj;
     }
-    for (int b0 = 0; b0 < nslots; b0 += Bc) {
-        const int bc = (nslots - b0) < Bc ? (nslots - b0) : Bc;
+    for (int b0 = slot0; b0 < slot0 + nslots; b0 += Bc) {
+        const int bc = (slot0 + nslots - b0) < Bc ? (slot0 + nslots - b0) : Bc;
         rt.b0 = b0;
         DView dD{D, (u64)L * N, 0};
         DView spec{ACC + (size_t)L * N, (u64)(L + 1) * N, 0};             // special-prime limb of every (b,k)
@@ -586,6 +586,34 @@ static KsRoute uniform_route(const ckks_view *in, const ckks_view *out, const ui
     return rt;
 }
 
+// A batch of 16 or more key switches is split into two halves that run as concurrent pipelines on the
+// lanes' streams (fork/join with events on the caller's stream): the short kernels of one half overlap
+// the long kernels of the other.
+static int keyswitch_lanes(ckks_ctx *c, int mode, int L, int nslots, const KsRoute &rt, cudaStream_t st) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (nslots < 16 || c->chain_lanes < 2 || cap != cudaStreamCaptureStatusNone) return keyswitch(c, mode, L, nslots, rt, st);
+    int rc;
+    const int half = nslots / 2;
+    for (int li = 0; li < 2; li++) {
+        const int cnt = li == 0 ? half : nslots - half;
+        if ((rc = ensure_lane(c, li, ks_words_per_ct(c, L) * 8 * (size_t)ks_chunk(c, cnt, L)))) return rc;
+    }
+    if (!c->ev_in) {
+        CU(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(c->ev_in, st));
+    for (int li = 0; li < 2; li++) {
+        ckks_ctx::Lane &ln = c->lane[li];
+        CU(cudaStreamWaitEvent(ln.main, c->ev_in, 0));
+        if ((rc = keyswitch(c, mode, L, li == 0 ? half : nslots - half, rt, ln.main, false, li, li == 0 ? 0 : half))) return rc;
+        CU(cudaEventRecord(ln.end, ln.main));
+        CU(cudaStreamWaitEvent(st, ln.end, 0));
+    }
+    return CKKS_OK;
+}
+
 extern "C" int ckks_relinearize(ckks_ctx *c, const ckks_view *in, const uint64_t *rlk, const ckks_view *out, ckks_stream s) {
     int rc;
     if ((rc = check_view(c, in, "encrypted")) || (rc = check_view(c, out, "out"))) return rc;
@@ -596,7 +624,7 @@ extern "C" int ckks_relinearize(ckks_ctx *c, const ckks_view *in, const uint64_t
     if (out->data == in->data && (out->poly_stride != in->poly_stride || out->batch_stride != in->batch_stride))
         return fail(CKKS_ERR_INVALID, "relinearize: in-place only with identical strides");
     CU(cudaSetDevice(c->device));
-    return keyswitch(c, 1, in->limbs, in->batch, uniform_route(in, out, nullptr, rlk), (cudaStream_t)s);
+    return keyswitch_lanes(c, 1, in->limbs, in->batch, uniform_route(in, out, nullptr, rlk), (cudaStream_t)s);
 }
 
 extern "C" int ckks_apply_galois(ckks_ctx *c, const ckks_view *in, uint64_t g, const uint64_t *gk, const ckks_view *out, ckks_stream s) {
@@ -610,7 +638,7 @@ extern "C" int ckks_apply_galois(ckks_ctx *c, const ckks_view *in, uint64_t g, c
     const uint32_t *perm = nullptr;
     if ((rc = get_perm(c, g, &perm))) return rc;
     CU(cudaSetDevice(c->device));
-    return keyswitch(c, 2, in->limbs, in->batch, uniform_route(in, out, perm, gk), (cudaStream_t)s);
+    return keyswitch_lanes(c, 2, in->limbs, in->batch, uniform_route(in, out, perm, gk), (cudaStream_t)s);
 }
 
 extern "C" int ckks_keyset_create(ckks_ctx *c, ckks_keyset **out) {
@@ -924,7 +952,7 @@ extern "C" int ckks_rotate_plan(ckks_ctx *c, const ckks_rotplan *p, const ckks_v
     }
     for (size_t r = 0; r < p->round_cnt.size(); r++) {
         rt.sel = p->d_sel + p->round_off[r];
-        if ((rc = keyswitch(c, 2, in->limbs, p->round_cnt[r], rt, st))) return rc;
+        if ((rc = keyswitch_lanes(c, 2, in->limbs, p->round_cnt[r], rt, st))) return rc;
     }
     return CKKS_OK;
 }
