@@ -254,3 +254,45 @@ def test_full_size_properties_n32768(make_fixture):
                 c = fx.orc.intt(j, np.array(diff, dtype=np.uint64)).astype(object)
                 c = np.where(c > p // 2, c - p, c)
                 assert np.abs(c).max() < 2 ** 24, (step, i, j)
+
+
+@pytest.mark.parametrize("batch,count", [(1, 1), (3, 4), (5, 9), (16, 6), (19, 7), (33, 12)])
+def test_rotate_sum_chain_matches_sequential(make_fixture, batch, count):
+    """ckks_rotate_sum_chain (fused add, CUDA-graph replay, two concurrent lanes for batches >= 16)
+    equals `count` sequential rotate_vector + add_inplace steps of the oracle (helper.h:472-476)"""
+    fx = make_fixture(12, CHAINS[12])
+    rng = np.random.default_rng(100 + batch)
+    L = 2
+    dup0 = fx.random_ct(rng, batch, 2, L)
+    acc0 = fx.random_ct(rng, batch, 2, L)
+    g = fx.orc.galois_elt(1)
+    want_acc, want_dup = [], []
+    for b in range(batch):
+        d, a = dup0[b], acc0[b]
+        for _ in range(count):
+            d = fx.orc.apply_galois(d, g, fx.gks[g])
+            a = fx.orc.add(a, d)
+        want_acc.append(a)
+        want_dup.append(d)
+    dup, acc = fx.ctx.upload(dup0), fx.ctx.upload(acc0)
+    for _ in range(2):                      # second round replays the cached graphs on fresh data
+        dup.data.copy_(fx.ctx.upload(dup0).data)
+        acc.data.copy_(fx.ctx.upload(acc0).data)
+        last = fx.ev.rotate_sum_chain(dup, acc, 1, count, fx.keys)
+        assert np.array_equal(acc.numpy(), np.stack(want_acc))
+        assert np.array_equal(last.numpy(), np.stack(want_dup))
+
+
+def test_large_batch_two_lanes_matches_oracle(make_fixture):
+    """batches of 16+ run as two concurrent half-batch pipelines; every entry still equals the oracle"""
+    fx = make_fixture(12, CHAINS[12])
+    rng = np.random.default_rng(77)
+    a = fx.random_ct(rng, 37, 2, fx.L)
+    a3 = fx.random_ct(rng, 21, 3, fx.L)
+    g = fx.orc.galois_elt(-8)
+    got = fx.ev.apply_galois(fx.ctx.upload(a), g, fx.keys).numpy()
+    for i in range(37):
+        assert np.array_equal(got[i], fx.orc.apply_galois(a[i], g, fx.gks[g])), i
+    got = fx.ev.relinearize(fx.ctx.upload(a3), fx.keys).numpy()
+    for i in range(21):
+        assert np.array_equal(got[i], fx.orc.relinearize(a3[i], fx.rlk)), i
