@@ -64,6 +64,29 @@ __device__ __forceinline__ void load_perm8(unsigned (&ix)[8], const uint32_t *pe
 // predecessor's results
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ---- TMA 1-D bulk copy global -> shared with mbarrier completion (SASS: UBLKCP), used to stage the
+// next digit's 16 KB tile while the current digit is transformed
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_tile(void *dst, const void *src, unsigned bytes, u64 *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Per-entry routing of a batched key switch: which ciphertext of the views a launch slot works
@@ -322,7 +345,9 @@ struct JjList {
 template <int LOGN, bool GALOIS>
 __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, Tables t) {
     typedef NttGeo<LOGN> G;
-    __shared__ u64 smem[NTT_TILE];
+    // TMA-staged input tiles of the current / next digit; the current one doubles as the exchange buffer
+    __shared__ __align__(128) u64 stage[2][NTT_TILE];
+    __shared__ u64 bars[2];
     pdl_launch_dependents();
     const int jj = list.jj[blockIdx.y], b = blockIdx.z;
     const KsSel sl = route_sel(rt, b);
@@ -336,7 +361,19 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
     u64 lo0[8], hi0[8], lo1[8], hi1[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) lo0[e] = hi0[e] = lo1[e] = hi1[e] = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+    }
+    __syncthreads();
     pdl_wait();
+    // digits that need a transform, in order; their tiles are fetched one ahead by TMA
+    auto tile_of = [&](int i) { return T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N + t0; };
+    int nxt = 0;                       // next digit whose tile has not been requested yet
+    while (nxt < L && nxt == pj) nxt++;
+    unsigned ph[2] = {0, 0};
+    int slot = 0;
+    if (threadIdx.x == 0 && nxt < L) tma_load_tile(stage[0], tile_of(nxt), NTT_TILE * 8, &bars[0]);
     for (int i = 0; i < L; i++) {
         u64 x[8];
         // the key stream comes from HBM: start it before the transform of this digit
@@ -353,11 +390,18 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
                 load8(x, in + t0 + 8 * threadIdx.x);
             }
         } else {
-            const u64 *in = T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N;
+            // this digit's tile was requested one iteration ago; request the following one now
+            int after = i + 1;
+            while (after < L && after == pj) after++;
+            __syncthreads();  // every thread is done with the other stage buffer (previous digit's exchanges)
+            if (threadIdx.x == 0 && after < L) tma_load_tile(stage[slot ^ 1], tile_of(after), NTT_TILE * 8, &bars[slot ^ 1]);
+            mbar_wait(&bars[slot], ph[slot]);
+            ph[slot] ^= 1;
 #pragma unroll
-            for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
-            __syncthreads();  // previous iteration's shared-memory reads are done
-            fwd_row_pass<LOGN>(x, tw, m, t0, smem);
+            for (int e = 0; e < 8; e++) x[e] = stage[slot][row_strided_li<LOGN>(e)];
+            __syncthreads();  // tile consumed: the buffer now serves as the exchange buffer of the transform
+            fwd_row_pass<LOGN>(x, tw, m, t0, stage[slot]);
+            slot ^= 1;
         }
         const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
         const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
@@ -389,7 +433,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
 template <int LOGN, bool GALOIS>
 __global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, Tables t) {
     typedef NttGeo<LOGN> G;
-    __shared__ u64 smem[NTT_TILE];
+    __shared__ __align__(128) u64 stage[2][NTT_TILE];   // TMA-staged tiles; the current one is also the exchange buffer
+    __shared__ u64 bars[2];
     pdl_launch_dependents();
     const int jj = list.jj[blockIdx.y], b = blockIdx.z;
     const KsSel sl = route_sel(rt, b);
@@ -403,7 +448,18 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsR
     double a0[8], a1[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) a0[e] = a1[e] = 0.0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+    }
+    __syncthreads();
     pdl_wait();
+    auto tile_of = [&](int i) { return T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N + t0; };
+    int nxt = 0;
+    while (nxt < L && nxt == pj) nxt++;
+    unsigned ph[2] = {0, 0};
+    int slot = 0;
+    if (threadIdx.x == 0 && nxt < L) tma_load_tile(stage[0], tile_of(nxt), NTT_TILE * 8, &bars[0]);
     for (int i = 0; i < L; i++) {
         double x[8];
         prefetch_l2(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
@@ -422,11 +478,17 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsR
 #pragma unroll
             for (int e = 0; e < 8; e++) x[e] = fp_from_u64(xi[e]);
         } else {
-            const u64 *in = T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N;
-#pragma unroll
-            for (int e = 0; e < 8; e++) x[e] = bits_fp(in[t0 + row_strided_li<LOGN>(e)]);
+            int after = i + 1;
+            while (after < L && after == pj) after++;
             __syncthreads();
-            fwd_row_pass_fp<LOGN>(x, tw, f, t0, as_fp(smem));   // lazy, |x| < 32p
+            if (threadIdx.x == 0 && after < L) tma_load_tile(stage[slot ^ 1], tile_of(after), NTT_TILE * 8, &bars[slot ^ 1]);
+            mbar_wait(&bars[slot], ph[slot]);
+            ph[slot] ^= 1;
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = bits_fp(stage[slot][row_strided_li<LOGN>(e)]);
+            __syncthreads();
+            fwd_row_pass_fp<LOGN>(x, tw, f, t0, as_fp(stage[slot]));   // lazy, |x| < 32p
+            slot ^= 1;
         }
         const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
         const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
