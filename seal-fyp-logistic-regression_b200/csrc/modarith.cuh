@@ -160,16 +160,21 @@ __device__ __forceinline__ double fp_rint(double v) {   // round to nearest inte
     const double M = 6755399441055744.0;                 // 1.5 * 2^52
     return __dadd_rn(__dadd_rn(v, M), -M);
 }
+// rint(a*b) with the product, the magic-number add and the rounding in one FMA, |a*b| < 2^51
+__device__ __forceinline__ double fp_rint_mul(double a, double b) {
+    const double M = 6755399441055744.0;
+    return __dadd_rn(__fma_rn(a, b, M), -M);
+}
 __device__ __forceinline__ double fp_mulmod(double y, double w, const FpConst &f) {
     double h = __dmul_rn(w, y);
     double l = __fma_rn(w, y, -h);
-    double q = fp_rint(__dmul_rn(h, f.pinv));
+    double q = fp_rint_mul(h, f.pinv);
     double r = __fma_rn(-q, f.p, h);
     return __dadd_rn(r, l);
 }
 // x -> representative in about (-p/2, p/2)
 __device__ __forceinline__ double fp_reduce(double x, const FpConst &f) {
-    double q = fp_rint(__dmul_rn(x, f.pinv));
+    double q = fp_rint_mul(x, f.pinv);
     return __fma_rn(-q, f.p, x);
 }
 // exact conversions for integers below 2^52
