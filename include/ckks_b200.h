@@ -185,6 +185,21 @@ int ckks_rescale(ckks_ctx *ctx, const ckks_view *in, const ckks_view *out, ckks_
  * out share storage and strides this is a no-op (the caller only lowers `limbs`). */
 int ckks_mod_switch_drop(ckks_ctx *ctx, const ckks_view *in, const ckks_view *out, ckks_stream s);
 
+/* ---- CKKSEncoder on the device (tolerance-compared) --------------------------------
+ * CKKSEncoder::encode(const vector<double>&, double scale, Plaintext&)
+ * (linear_transformation2.cpp:328-330, logistic_regression_ckks.cpp:225,305,590-611), batched: `values` is a
+ * DEVICE array [out->batch][count] of doubles, count <= N/2 (the remaining slots are zero, as in
+ * SEAL); `out` is a size-1 view (plaintext) with out->limbs limbs and receives NTT form. */
+int ckks_encode(ckks_ctx *ctx, const double *values, int count, double scale, const ckks_view *out,
+                ckks_stream s);
+/* CKKSEncoder::encode(double value, double scale, Plaintext&) (logistic_regression_ckks.cpp:78,157,331):
+ * the same constant in every slot, every batch entry of `out`. */
+int ckks_encode_scalar(ckks_ctx *ctx, double value, double scale, const ckks_view *out, ckks_stream s);
+/* CKKSEncoder::decode(const Plaintext&, vector<double>&) (linear_transformation2.cpp:384,
+ * logistic_regression_ckks.cpp:365,499): `in` is a size-1 view at any level, `values` a DEVICE array
+ * [in->batch][N/2] receiving the real parts of the slots.  `in` is not modified. */
+int ckks_decode(ckks_ctx *ctx, const ckks_view *in, double scale, double *values, ckks_stream s);
+
 #ifdef __cplusplus
 }
 #endif

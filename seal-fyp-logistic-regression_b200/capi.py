@@ -86,6 +86,9 @@ SIGNATURES = {
     "ckks_multiply_sum": (C.c_int, [C.c_void_p, _VP, _VP, _VP, C.c_void_p]),
     "ckks_rescale": (C.c_int, [C.c_void_p, _VP, _VP, C.c_void_p]),
     "ckks_mod_switch_drop": (C.c_int, [C.c_void_p, _VP, _VP, C.c_void_p]),
+    "ckks_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, _VP, C.c_void_p]),
+    "ckks_encode_scalar": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _VP, C.c_void_p]),
+    "ckks_decode": (C.c_int, [C.c_void_p, _VP, C.c_double, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

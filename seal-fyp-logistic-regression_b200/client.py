@@ -64,8 +64,23 @@ class CKKSEncoder:
         return out
 
     def encode(self, values, scale, limbs=None):
-        """encode(vector<double>) or encode(double) -> Plaintext (NTT form, on device).
-        A 2-D `values` array gives one plaintext per row (a batch)."""
+        """encode(vector<double>) or encode(double) -> Plaintext (NTT form, on device): the
+        embedding DFT, rounding, RNS reduction and NTT all run on the GPU (ckks_encode).
+        A 2-D `values` array (numpy or CUDA tensor) gives one plaintext per row (a batch)."""
+        if np.isscalar(values):
+            return self.ev.encode_scalar(float(values), scale, limbs)
+        if not torch.is_tensor(values):
+            values = torch.from_numpy(np.atleast_2d(np.asarray(values, dtype=np.float64)))
+        if values.dim() == 2 and values.shape[1] > self.slots:
+            values = values[:, : self.slots]
+        return self.ev.encode(values, scale, limbs)
+
+    def decode(self, pt):
+        """Plaintext (batch B) -> float64 [B][slots] (numpy), computed on the GPU (ckks_decode)"""
+        return self.ev.decode(pt).cpu().numpy()
+
+    def encode_host(self, values, scale, limbs=None):
+        """numpy restatement of encode (host FFT + device NTT); kept as a cross-check of the device path"""
         limbs = self.ctx.top_limbs if limbs is None else limbs
         n = self.ctx.n
         if np.isscalar(values):
@@ -88,8 +103,8 @@ class CKKSEncoder:
         self.ev.ntt_forward(pt.data.view(B, limbs, n))
         return pt
 
-    def decode(self, pt):
-        """Plaintext (batch B) -> float64 [B][slots]"""
+    def decode_host(self, pt):
+        """numpy restatement of decode (device INTT + host CRT/FFT); cross-check of the device path"""
         n, L = self.ctx.n, pt.limbs
         t = pt.data[:, 0, :L, :].clone()          # the inverse NTT runs in place: keep the plaintext intact
         self.ev.ntt_inverse(t)

@@ -5,6 +5,7 @@
 // and nothing falls back to the CPU.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -14,6 +15,7 @@
 
 #include "../../include/ckks_b200.h"
 #include "kernels.cuh"
+#include "encoder.cuh"
 #include "tables.h"
 
 // ------------------------------------------------------------------------------------ errors
@@ -63,6 +65,8 @@ struct ckks_ctx {
     void *d_mod = nullptr, *d_twf = nullptr, *d_twi = nullptr, *d_inv = nullptr, *d_invs = nullptr, *d_half = nullptr;
     void *d_fp = nullptr, *d_twfd = nullptr, *d_twid = nullptr;
     std::unordered_map<uint64_t, uint32_t *> perms;
+    uint32_t *d_kidx = nullptr;                 // encoder: slot i -> DFT position (3^i mod 2N - 1)/2
+    std::vector<HalfDigits> half_digits;        // decoder: mixed-radix digits of (Q_L - 1)/2, index L
     u64 *ws = nullptr;
     size_t ws_bytes = 0;
     size_t ws_cap = size_t(1) << 30;
@@ -174,6 +178,7 @@ extern "C" void ckks_ctx_destroy(ckks_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto &kv : c->perms) cudaFree(kv.second);
+    cudaFree(c->d_kidx);
     for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
     if (c->chain_stream) cudaStreamDestroy(c->chain_stream);
     for (auto &ln : c->lane) {
@@ -1020,6 +1025,168 @@ extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *o
         launch_pdl(k_md_fwd_row<LN, 0>, dim3(G::ROW_TILES, Lo, bc * S), st, T2, src, rrt, S, Lo, Lo, c->t); \
         LAUNCH_CHECK(c);                                                                                          \
     }
+        DISPATCH_LOGN(c, RUN)
+#undef RUN
+    }
+    return CKKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ encoder
+static int ensure_encoder_tables(ckks_ctx *c) {
+    if (c->d_kidx) return CKKS_OK;
+    const uint32_t n = (uint32_t)c->n, m = 2 * n;
+    std::vector<uint32_t> k(n / 2);
+    uint64_t pos = 1;
+    for (uint32_t i = 0; i < n / 2; i++) {
+        k[i] = (uint32_t)((pos - 1) >> 1);
+        pos = pos * 3 % m;
+    }
+    int rc = upload_vec((void **)&c->d_kidx, k.data(), k.size() * sizeof(uint32_t));
+    if (rc) return rc;
+    // (Q_L - 1)/2 in the mixed radix q_0, q_1, ...: little-endian multi-word arithmetic on the host
+    c->half_digits.assign(c->K + 1, HalfDigits{});
+    for (int L = 1; L <= c->K; L++) {
+        std::vector<uint64_t> big{1};
+        for (int i = 0; i < L; i++) {   // big *= q_i
+            unsigned __int128 carry = 0;
+            for (auto &w : big) {
+                unsigned __int128 v = (unsigned __int128)w * c->primes[i] + carry;
+                w = (uint64_t)v;
+                carry = v >> 64;
+            }
+            if (carry) big.push_back((uint64_t)carry);
+        }
+        big[0] -= 1;                     // Q is odd
+        for (size_t w = 0; w < big.size(); w++)   // >>= 1
+            big[w] = (big[w] >> 1) | (w + 1 < big.size() ? big[w + 1] << 63 : 0);
+        for (int i = 0; i < L; i++) {   // digit = big mod q_i; big /= q_i
+            unsigned __int128 rem = 0;
+            for (size_t w = big.size(); w-- > 0;) {
+                unsigned __int128 cur = (rem << 64) | big[w];
+                big[w] = (uint64_t)(cur / c->primes[i]);
+                rem = cur % c->primes[i];
+            }
+            c->half_digits[L].d[i] = (uint64_t)rem;
+        }
+    }
+    return CKKS_OK;
+}
+
+template <int SGN>
+static int run_fft(ckks_ctx *c, double2 *v, int batch, cudaStream_t st) {
+#define RUN(LN)                                                                                          \
+    {                                                                                                    \
+        k_fft_top<LN, SGN><<<dim3(FFT_TILE / 256, batch), 256, 0, st>>>(v); LAUNCH_CHECK(c);             \
+        k_fft_tile<SGN><<<dim3((1 << LN) / FFT_TILE, batch), 256, 0, st>>>(v, 1 << LN); LAUNCH_CHECK(c); \
+    }
+    DISPATCH_LOGN(c, RUN)
+#undef RUN
+    return CKKS_OK;
+}
+
+static int encoder_chunk(const ckks_ctx *c, int batch, size_t bytes_per_entry) {
+    size_t fit = c->ws_cap / bytes_per_entry;
+    if (fit < 1) fit = 1;
+    if (fit > 65535) fit = 65535;
+    return (int)(fit < (size_t)batch ? fit : (size_t)batch);
+}
+
+extern "C" int ckks_encode(ckks_ctx *c, const double *values, int count, double scale, const ckks_view *out, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, out, "plain"))) return rc;
+    if (out->size != 1) return fail(CKKS_ERR_INVALID, "encode: destination must be a plaintext (size 1)");
+    if (count < 0 || count > c->n / 2) return fail(CKKS_ERR_INVALID, "values has invalid size");
+    if (count > 0 && !values) return fail(CKKS_ERR_INVALID, "encode: null values");
+    if (!(scale > 0.0)) return fail(CKKS_ERR_INVALID, "scale out of bounds");
+    if (out->batch > 1 && out->batch_stride == 0) return fail(CKKS_ERR_INVALID, "encode: destination entries must be distinct");
+    CU(cudaSetDevice(c->device));
+    if ((rc = ensure_encoder_tables(c))) return rc;
+    cudaStream_t st = (cudaStream_t)s;
+    const size_t N = c->n;
+    const int B = out->batch, Bc = encoder_chunk(c, B, N * sizeof(double2));
+    if ((rc = ensure_ws(c, (size_t)Bc * N * sizeof(double2)))) return rc;
+    double2 *v = (double2 *)c->ws;
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int bc = (B - b0) < Bc ? (B - b0) : Bc;
+        k_enc_scatter<<<dim3((unsigned)(N / 2 + 255) / 256, bc), 256, 0, st>>>(values + (size_t)b0 * count, count, c->d_kidx, v, (int)N);
+        LAUNCH_CHECK(c);
+        if ((rc = run_fft<-1>(c, v, bc, st))) return rc;
+        DView dst{(u64 *)out->data + (u64)b0 * out->batch_stride, out->batch_stride, out->poly_stride};
+#define RUN(LN) k_enc_round<LN><<<dim3((1 << LN) / 256, bc), 256, 0, st>>>(v, scale / (double)N, dst, out->limbs, c->t); LAUNCH_CHECK(c);
+        DISPATCH_LOGN(c, RUN)
+#undef RUN
+        // plaintexts live in NTT form: transform the bc x limbs coefficient limbs in place
+        if ((rc = ntt_api(c, (uint64_t *)dst.data, bc, out->limbs, 0, B > 1 ? out->batch_stride : out->poly_stride, false, st))) return rc;
+    }
+    return CKKS_OK;
+}
+
+static uint64_t host_residue(double r, uint64_t p) {
+    const bool neg = r < 0.0;
+    double a = neg ? -r : r;
+    uint64_t res;
+    if (a < 4611686018427387904.0) {
+        res = (uint64_t)a % p;
+    } else {
+        int e;
+        const double fr = frexp(a, &e);
+        const uint64_t mant = (uint64_t)ldexp(fr, 53);
+        e -= 53;
+        unsigned __int128 pw = 1, base = 2;
+        for (; e > 0; e >>= 1) {
+            if (e & 1) pw = pw * base % p;
+            base = base * base % p;
+        }
+        res = (uint64_t)((unsigned __int128)(mant % p) * pw % p);
+    }
+    return (neg && res) ? p - res : res;
+}
+
+extern "C" int ckks_encode_scalar(ckks_ctx *c, double value, double scale, const ckks_view *out, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, out, "plain"))) return rc;
+    if (out->size != 1) return fail(CKKS_ERR_INVALID, "encode: destination must be a plaintext (size 1)");
+    if (!(scale > 0.0)) return fail(CKKS_ERR_INVALID, "scale out of bounds");
+    if (out->limbs > 32) return fail(CKKS_ERR_INVALID, "encode: more than 32 limbs");
+    CU(cudaSetDevice(c->device));
+    ConstResidues cr{};
+    const double r = nearbyint(value * scale);
+    for (int l = 0; l < out->limbs; l++) cr.r[l] = host_residue(r, c->primes[l]);
+    k_enc_fill<<<dim3((c->n + 255) / 256, out->limbs, out->batch), 256, 0, (cudaStream_t)s>>>(dv(out), cr, c->n);
+    LAUNCH_CHECK(c);
+    return CKKS_OK;
+}
+
+extern "C" int ckks_decode(ckks_ctx *c, const ckks_view *in, double scale, double *values, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, in, "plain"))) return rc;
+    if (in->size != 1) return fail(CKKS_ERR_INVALID, "decode: source must be a plaintext (size 1)");
+    if (!values) return fail(CKKS_ERR_INVALID, "decode: null destination");
+    if (!(scale > 0.0)) return fail(CKKS_ERR_INVALID, "scale out of bounds");
+    if (in->limbs > 32) return fail(CKKS_ERR_INVALID, "decode: more than 32 limbs");
+    if (in->batch > 1 && in->batch_stride == 0) return fail(CKKS_ERR_INVALID, "decode: broadcast views are not supported");
+    CU(cudaSetDevice(c->device));
+    if ((rc = ensure_encoder_tables(c))) return rc;
+    cudaStream_t st = (cudaStream_t)s;
+    const size_t N = c->n;
+    const int B = in->batch, L = in->limbs;
+    const size_t per = N * sizeof(double2) + (size_t)L * N * 8;
+    const int Bc = encoder_chunk(c, B, per);
+    if ((rc = ensure_ws(c, per * Bc))) return rc;
+    double2 *v = (double2 *)c->ws;
+    u64 *res = c->ws + (size_t)Bc * N * 2;
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int bc = (B - b0) < Bc ? (B - b0) : Bc;
+        // the inverse transform runs in place: work on a copy of the plaintext limbs
+        CU(cudaMemcpy2DAsync(res, (size_t)L * N * 8, (const u64 *)in->data + (u64)b0 * in->batch_stride,
+                             (size_t)(B > 1 ? in->batch_stride : in->poly_stride) * 8, (size_t)L * N * 8, bc,
+                             cudaMemcpyDeviceToDevice, st));
+        if ((rc = ntt_api(c, (uint64_t *)res, bc, L, 0, (uint64_t)L * N, true, st))) return rc;
+#define RUN(LN) k_dec_compose<LN><<<dim3((1 << LN) / 256, bc), 256, 0, st>>>(res, L, c->half_digits[L], 1.0 / scale, v, c->t); LAUNCH_CHECK(c);
+        DISPATCH_LOGN(c, RUN)
+#undef RUN
+        if ((rc = run_fft<1>(c, v, bc, st))) return rc;
+#define RUN(LN) k_dec_gather<LN><<<dim3((1 << LN) / 512, bc), 256, 0, st>>>(v, c->d_kidx, values + (size_t)b0 * (N / 2)); LAUNCH_CHECK(c);
         DISPATCH_LOGN(c, RUN)
 #undef RUN
     }

@@ -376,6 +376,39 @@ class Evaluator:
             raise capi.CkksInvalidArgument("cannot switch to higher level modulus")
         return Ciphertext(x.ctx, x.data, limbs, x.scale)
 
+    # ---- CKKSEncoder on the device (include/ckks_b200.h: ckks_encode / ckks_encode_scalar / ckks_decode)
+    def encode(self, values, scale, limbs=None, cap=None):
+        """CKKSEncoder::encode(vector<double>, scale, plain), batched: `values` is a float64 CUDA
+        tensor [B][count] (count <= N/2); returns a batch of B plaintexts in NTT form."""
+        ctx = self.ctx
+        limbs = ctx.top_limbs if limbs is None else limbs
+        if values.dim() == 1:
+            values = values[None]
+        values = values.to(device=ctx.device, dtype=torch.float64).contiguous()
+        if values.shape[1] > ctx.n // 2:
+            raise capi.CkksInvalidArgument("values has invalid size")
+        out = ctx.empty(values.shape[0], 1, limbs, cap=cap, scale=scale)
+        vo = out.view()
+        check(self.lib.ckks_encode(self.h, values.data_ptr(), values.shape[1], float(scale), C.byref(vo), _stream()))
+        return out
+
+    def encode_scalar(self, value, scale, limbs=None, batch=1, cap=None):
+        """CKKSEncoder::encode(double, scale, plain): the same constant in every slot"""
+        limbs = self.ctx.top_limbs if limbs is None else limbs
+        out = self.ctx.empty(batch, 1, limbs, cap=cap, scale=scale)
+        vo = out.view()
+        check(self.lib.ckks_encode_scalar(self.h, float(value), float(scale), C.byref(vo), _stream()))
+        return out
+
+    def decode(self, pt):
+        """CKKSEncoder::decode(plain, vector<double>&) -> float64 CUDA tensor [B][N/2]"""
+        if pt.data.shape[1] != 1:
+            raise capi.CkksInvalidArgument("decode expects plaintexts (size 1)")
+        out = torch.empty((pt.batch, self.ctx.n // 2), dtype=torch.float64, device=self.ctx.device)
+        vi = pt.view()
+        check(self.lib.ckks_decode(self.h, C.byref(vi), float(pt.scale), out.data_ptr(), _stream()))
+        return out
+
     # ---- raw NTT (tests / encoder)
     def ntt_forward(self, tensor, first_prime=0):
         """tensor: [P][L][N] int64, limb l uses prime first_prime + l; in place"""

@@ -653,22 +653,7 @@ private:
 class CKKSEncoder {
 public:
     template <class Ctx>
-    explicit CKKSEncoder(const Ctx &context) : e_(detail::engine_of(context)) {
-        std::size_t n = e_->n, slots = n / 2;
-        pos_.resize(n);
-        std::uint64_t v = 1;
-        for (std::size_t i = 0; i < slots; i++) {
-            pos_[i] = detail::bitrev((std::uint32_t)((v - 1) >> 1), e_->log_n);
-            pos_[slots + i] = detail::bitrev((std::uint32_t)((2 * n - v - 1) >> 1), e_->log_n);
-            v = v * 3 % (2 * n);
-        }
-        roots_.resize(n);
-        const double pi = std::acos(-1.0);
-        for (std::size_t i = 0; i < n; i++) {
-            double ang = 2.0 * pi * (double)detail::bitrev((std::uint32_t)i, e_->log_n) / (double)(2 * n);
-            roots_[i] = std::complex<double>(std::cos(ang), std::sin(ang));
-        }
-    }
+    explicit CKKSEncoder(const Ctx &context) : e_(detail::engine_of(context)) {}
     std::size_t slot_count() const { return e_->n / 2; }
 
     void encode(const std::vector<double> &values, parms_id_type id, double scale, Plaintext &dst, MemoryPoolHandle = {}) {
@@ -682,121 +667,56 @@ public:
     }
     void encode(double value, double scale, Plaintext &dst, MemoryPoolHandle = {}) { encode_const(value, e_->K - 1, scale, dst); }
 
+    // inverse NTT, CRT composition, embedding DFT and slot gather all run on the device (ckks_decode)
     void decode(const Plaintext &plain, std::vector<double> &out, MemoryPoolHandle = {}) {
         const detail::Poly &p = plain.poly();
         if (!p.buf) throw std::invalid_argument("plain is not valid for encryption parameters");
-        std::size_t n = e_->n, slots = n / 2;
-        int L = p.limbs;
-        auto tmp = std::make_shared<detail::DevBuf>(e_, (std::size_t)L * n);
-        detail::check(ckks_copy(e_->ctx, tmp->p, p.buf->p, (std::size_t)L * n * 8, nullptr));
-        detail::check(ckks_ntt_inverse(e_->ctx, tmp->p, 1, L, 0, (std::uint64_t)L * n, nullptr));
-        std::vector<std::uint64_t> h((std::size_t)L * n);
-        detail::check(ckks_download(e_->ctx, h.data(), tmp->p, h.size() * 8, nullptr));
-        detail::check(ckks_stream_sync(e_->ctx, nullptr));
-        // CRT composition by Garner's mixed-radix digits, centred, as long double
-        std::vector<std::uint64_t> inv(L);
-        std::vector<long double> radix(L);
-        for (int k = 0; k < L; k++) {
-            std::uint64_t pk = e_->primes[k], prod = 1 % pk;
-            for (int i = 0; i < k; i++) prod = detail::mulmod(prod, e_->primes[i] % pk, pk);
-            inv[k] = detail::powmod(prod, pk - 2, pk);
-            radix[k] = k ? radix[k - 1] * (long double)e_->primes[k - 1] : 1.0L;
-        }
-        std::vector<std::complex<double>> vals(n);
-        std::vector<std::uint64_t> dg(L);
-        for (std::size_t q = 0; q < n; q++) {
-            for (int k = 0; k < L; k++) {
-                std::uint64_t pk = e_->primes[k], acc = 0, mult = 1 % pk;
-                for (int i = 0; i < k; i++) {
-                    acc = (acc + detail::mulmod(dg[i] % pk, mult, pk)) % pk;
-                    mult = detail::mulmod(mult, e_->primes[i] % pk, pk);
-                }
-                std::uint64_t x = h[(std::size_t)k * n + q];
-                dg[k] = detail::mulmod((x + pk - acc) % pk, inv[k], pk);
-            }
-            bool neg = dg[L - 1] >= (e_->primes[L - 1] + 1) / 2;
-            if (neg) {
-                for (int k = 0; k < L; k++) dg[k] = e_->primes[k] - 1 - dg[k];
-                for (int k = 0; k < L; k++) {
-                    if (++dg[k] < e_->primes[k]) break;
-                    dg[k] = 0;
-                }
-            }
-            long double v = 0;
-            for (int k = L - 1; k >= 0; k--) v += (long double)dg[k] * radix[k];
-            vals[q] = std::complex<double>((double)((neg ? -v : v) / (long double)p.scale), 0.0);
-        }
-        // forward negacyclic FFT (same butterfly structure as the NTT, zeta for psi)
-        std::size_t t = n >> 1;
-        for (std::size_t m = 1; m < n; m <<= 1, t >>= 1)
-            for (std::size_t i = 0; i < m; i++) {
-                std::complex<double> w = roots_[m + i];
-                for (std::size_t k = 2 * i * t; k < 2 * i * t + t; k++) {
-                    std::complex<double> u = vals[k], x = vals[k + t] * w;
-                    vals[k] = u + x;
-                    vals[k + t] = u - x;
-                }
-            }
+        std::size_t slots = e_->n / 2;
+        detail::DevBuf vals(e_, slots);
+        ckks_view v = p.view();
+        detail::check(ckks_decode(e_->ctx, &v, p.scale, reinterpret_cast<double *>(vals.p), nullptr));
         out.resize(slots);
-        for (std::size_t i = 0; i < slots; i++) out[i] = vals[pos_[i]].real();
+        detail::check(ckks_download(e_->ctx, out.data(), vals.p, slots * 8, nullptr));
+        detail::check(ckks_stream_sync(e_->ctx, nullptr));
     }
 
 private:
-    void finish(const std::vector<long double> &coeffs, int limbs, double scale, Plaintext &dst) {
-        std::size_t n = e_->n;
+    void check_target(double largest, int limbs, double scale) const {
         if (limbs < 1 || limbs > e_->K - 1) throw std::invalid_argument("parms_id is not valid for encryption parameters");
-        if (scale <= 0) throw std::invalid_argument("scale out of bounds");
-        std::vector<std::uint64_t> h((std::size_t)limbs * n);
-        for (std::size_t q = 0; q < n; q++) {
-            long double c = std::roundl(coeffs[q]);
-            bool neg = c < 0;
-            long double a = neg ? -c : c;
-            if (a >= 0x1p126L) throw std::invalid_argument("encoded values are too large");
-            detail::u128 mag = (detail::u128)a;
-            for (int j = 0; j < limbs; j++) {
-                std::uint64_t p = e_->primes[j], r = (std::uint64_t)(mag % p);
-                h[(std::size_t)j * n + q] = (neg && r) ? p - r : r;
-            }
-        }
+        if (!(scale > 0)) throw std::invalid_argument("scale out of bounds");
+        int bits = 0;
+        for (int j = 0; j < limbs; j++) bits += 64 - __builtin_clzll(e_->primes[j]);
+        if (std::log2(scale) >= bits) throw std::invalid_argument("scale out of bounds");
+        if (largest > 0 && std::log2(largest) + std::log2(scale) + 1 >= bits) throw std::invalid_argument("encoded values are too large");
+    }
+    // embedding DFT, rounding, RNS reduction and forward NTT on the device (ckks_encode)
+    void encode_impl(const std::vector<double> &values, int limbs, double scale, Plaintext &dst) {
+        std::size_t slots = e_->n / 2;
+        if (values.size() > slots) throw std::invalid_argument("values has invalid size");
+        double largest = 0;
+        for (double x : values) largest = std::max(largest, std::fabs(x));
+        check_target(largest, limbs, scale);
         detail::Poly &p = dst.poly();
         p.allocate(e_, 1, limbs);
         p.scale = scale;
-        detail::check(ckks_upload(e_->ctx, p.buf->p, h.data(), h.size() * 8, nullptr));
-        detail::check(ckks_stream_sync(e_->ctx, nullptr));
-    }
-    void encode_impl(const std::vector<double> &values, int limbs, double scale, Plaintext &dst) {
-        std::size_t n = e_->n, slots = n / 2;
-        if (values.size() > slots) throw std::invalid_argument("values has invalid size");
-        std::vector<std::complex<double>> v(n);
-        for (std::size_t i = 0; i < values.size(); i++) {
-            v[pos_[i]] = values[i];
-            v[pos_[slots + i]] = values[i];
+        ckks_view v = p.view();
+        if (values.empty()) {
+            detail::check(ckks_encode(e_->ctx, nullptr, 0, scale, &v, nullptr));
+            return;
         }
-        // inverse negacyclic FFT (Gentleman-Sande with conjugate roots), then 1/N
-        std::size_t t = 1;
-        for (std::size_t m = n >> 1; m >= 1; m >>= 1, t <<= 1)
-            for (std::size_t i = 0; i < m; i++) {
-                std::complex<double> w = std::conj(roots_[m + i]);
-                for (std::size_t k = 2 * i * t; k < 2 * i * t + t; k++) {
-                    std::complex<double> u = v[k], x = v[k + t];
-                    v[k] = u + x;
-                    v[k + t] = (u - x) * w;
-                }
-            }
-        std::vector<long double> coeffs(n);
-        for (std::size_t q = 0; q < n; q++) coeffs[q] = (long double)(v[q].real() / (double)n) * (long double)scale;
-        finish(coeffs, limbs, scale, dst);
-        detail::Poly &p = dst.poly();
-        detail::check(ckks_ntt_forward(e_->ctx, p.buf->p, 1, limbs, 0, (std::uint64_t)limbs * n, nullptr));
+        detail::DevBuf vals(e_, values.size());
+        detail::check(ckks_upload(e_->ctx, vals.p, values.data(), values.size() * 8, nullptr));
+        detail::check(ckks_encode(e_->ctx, reinterpret_cast<const double *>(vals.p), (int)values.size(), scale, &v, nullptr));
     }
     void encode_const(double value, int limbs, double scale, Plaintext &dst) {
-        // constant polynomial round(value * scale); its NTT is that constant in every position
-        std::vector<long double> coeffs(e_->n, (long double)value * (long double)scale);
-        finish(coeffs, limbs, scale, dst);
+        check_target(std::fabs(value), limbs, scale);
+        detail::Poly &p = dst.poly();
+        p.allocate(e_, 1, limbs);
+        p.scale = scale;
+        ckks_view v = p.view();
+        detail::check(ckks_encode_scalar(e_->ctx, value, scale, &v, nullptr));
     }
     std::shared_ptr<detail::Engine> e_;
-    std::vector<std::uint32_t> pos_;
-    std::vector<std::complex<double>> roots_;
 };
 
 // ------------------------------------------------------------------------------------ Encryptor / Decryptor
