@@ -171,7 +171,7 @@ class ColumnLayout:
 
 
 def column_epoch_gradient(ev, cols, labels, w_bcast, C, B, scale, keys, encoder, encryptor, degree=7,
-                          method="tree"):
+                          method="tree", dot_method="reference"):
     """One pass of the gradient loop over the mini-batches held by this GPU (column layout).
 
     cols    : batch M*C of column ciphertexts (entry m*C + j)
@@ -199,7 +199,7 @@ def column_epoch_gradient(ev, cols, labels, w_bcast, C, B, scale, keys, encoder,
     pred_labels = ev.sub(pred, lab)                                       # batch M
     colv = ev.mod_switch_to(cols, pred_labels.limbs)
     pl = Ciphertext(cols.ctx, pred_labels.data.repeat_interleave(C, dim=0), pred_labels.limbs, pred_labels.scale)
-    grads = cipher_dot_product(ev, colv, pl, B, keys)                     # M*C chains in lock-step
+    grads = cipher_dot_product(ev, colv, pl, B, keys, method=dot_method)  # M*C chains in lock-step
     masks = np.zeros((C, C))
     masks[np.arange(C), np.arange(C)] = 1.0
     mask_pt = encoder.encode(masks, scale, limbs=grads.limbs)

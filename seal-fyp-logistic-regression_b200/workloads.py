@@ -173,13 +173,28 @@ def _stack(cts):
 
 
 # ------------------------------------------------------------------ dot product
-def cipher_dot_product(ev, ctA, ctB, size, keys):
+def cipher_dot_product(ev, ctA, ctB, size, keys, method="reference"):
     """cipher_dot_product (helper.h:416-502), batched over independent (ctA[b], ctB[b]) pairs:
-    multiply, relinearize, rescale, rotate-and-sum over `size` slots, force the scale."""
+    multiply, relinearize, rescale, rotate-and-sum over `size` slots, force the scale.
+
+    method="reference" runs the reference's own sequence (size-1 dependent unit rotations; every
+    ciphertext polynomial bit-identical to SEAL's).  method="doubling" is the SURVEY 8(f4) upgrade:
+    the same cyclic sums from log2(size) rotations by 1, 2, 4, ... -- equal decrypted values within
+    noise, different polynomials, so it is a separate tolerance-checked mode and never the default."""
     mult = ev.multiply(ctA, ctB)
     mult = ev.relinearize(mult, keys)
     ev.rescale_to_next_inplace(mult)
     dup = ev.add(mult, ev.rotate_vector(mult, -size, keys))      # "vector has duplicate now"
+    if method == "doubling":
+        if size & (size - 1):
+            raise ValueError("the doubling rotate-and-sum needs a power-of-two size")
+        step = 1
+        while step < size:
+            dup = ev.add(dup, ev.rotate_vector(dup, step, keys))
+            step *= 2
+        return force_scale_pow2(dup)
+    if method != "reference":
+        raise ValueError("unknown rotate-and-sum method")
     # for i in 1..size-1: rotate_vector_inplace(dup, 1); add_inplace(mult, dup)   (helper.h:472-476)
     ev.rotate_sum_chain(dup, mult, 1, size - 1, keys)
     return force_scale_pow2(mult)

@@ -277,6 +277,14 @@ def test_column_layout_epoch_matches_plaintext(make_fixture):
     neww = lr.apply_gradient(ev, grad, wct, 0.1, R, scale, enc)
     got = enc.decode(decr.decrypt(neww))[0, :C]
     assert np.abs(got - lr.plain_epoch(X, y, w0, 0.1, degree)).max() < 1e-3
+    # SURVEY 8(f4) mode: log2(B) doubling rotations instead of B-1 unit rotations -- different
+    # polynomials, same decrypted gradient within noise
+    keys2 = kg.keyset(steps=[1, -16, 2, 4, 8])
+    fast = lr.column_epoch_gradient(ev, cols, labs, wb, C, B, scale, keys2, enc, encr, degree=degree, method="tree",
+                                    dot_method="doubling")
+    assert fast.limbs == grad.limbs and fast.scale == grad.scale
+    assert not np.array_equal(fast.numpy(), grad.numpy())
+    assert np.abs(enc.decode(decr.decrypt(fast))[0, :C] - g).max() < 1e-5
 
 
 def test_sparse_diagonal_sets_match_dense(make_fixture):
