@@ -45,6 +45,37 @@ def setup(log_n, bits, steps, seed=1):
     return ctx, ev, enc, keys, encr, decr
 
 
+def config1(results, R=2000, C=8):
+    """config 1: the reference's own LR program (row layout, degree-3 Horner sigmoid, lr 0.1,
+    logistic_regression_ckks.cpp:208-345) with repairs R1-R6, on a synthetic stand-in for the
+    2000 x 8 pulsar subset (standardised features), N = 32768, {60, 40 x 8, 60}"""
+    lrm = importlib.import_module(PKG + ".lr")
+    pow2 = [s for i in range(13) for s in (1 << i, -(1 << i))]
+    ctx, ev, enc, keys, encr, decr = setup(15, [60] + [40] * 8 + [60], pow2, seed=7)
+    rng = np.random.default_rng(1)
+    X = rng.normal(0, 1, (R, C))
+    wtrue = rng.uniform(-1, 1, C)
+    y = (1 / (1 + np.exp(-X @ wtrue)) > rng.uniform(0, 1, R)).astype(float)
+    w0 = rng.uniform(-2, 2, C)                                   # logistic_regression_ckks.cpp:552
+    lay = lrm.RowLayout(R, C, ctx.n // 2)
+    rows = encr.encrypt(enc.encode(lay.rows(X), SCALE))
+    cols = encr.encrypt(enc.encode(lay.columns(X), SCALE))
+    labs = encr.encrypt(enc.encode(lay.labels(y), SCALE))
+    wct = encr.encrypt(enc.encode(lay.weights(w0), SCALE))
+    ctx.reset_launch_count()
+    ms, neww = timed(lambda: lrm.update_weights(ev, rows, cols, labs, wct, 0.1, SCALE, keys, enc, encr, degree=3,
+                                                method="horner"), reps=1, warm=1)
+    launches = ctx.launch_count() // 2
+    got = enc.decode(decr.decrypt(neww))[0, :C]
+    want = lrm.plain_epoch(X, y, w0, 0.1, 3)
+    err = float(np.abs(got - want).max())
+    results["config1_lr_row_layout_R%d_N32768" % R] = {
+        "ms_per_iteration": ms, "iterations_per_s": 1e3 / ms, "kernel_launches": int(launches), "max_abs_err_vs_plain_lr": err,
+        "key_switches": R * (1 + 1 + C - 1) + C * (1 + 13 + R - 1) + 3,
+        "note": "one update_weights = one training iteration over all R rows; includes encoding the R one-hot masks on the device"}
+    print("config1 R=%d: %.1f ms per iteration, err %.2e" % (R, ms, err), flush=True)
+
+
 def config3(results):
     pow2 = [s for i in range(13) for s in (1 << i, -(1 << i))]
     ctx, ev, enc, keys, encr, decr = setup(14, [60, 40, 40, 60], pow2)
@@ -120,6 +151,11 @@ def config2(results):
 
 def main():
     results = {}
+    if "--only-config1" in sys.argv:
+        config1(results)
+        json.dump(results, open(os.path.join(ROOT, "gpurun_out", "r01_config1.json"), "w"), indent=1)
+        return
+    config1(results)
     config2(results)
     config3(results)
     config4(results, 5)
