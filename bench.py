@@ -403,6 +403,12 @@ def run_gpu(args):
                         "weights agree within noise; reported for information, the headline value is the reference "
                         "sequence" % (B_MINI, B_MINI - 1)}
 
+    # ---- config 3 beside the headline: Linear_Transform_Plain, N = 16384, d = 128, diagonals sharded
+    # over the ranks (interleaved), partial ciphertexts all-gathered and added mod q.  Strong scaling.
+    lt = None
+    if not args.no_lt:
+        lt = linear_transform_sharded(torch, eng, client, par, local, rank, world, timed)
+
     # ---- roofline of the dominant kernel family: the batched Galois key switch of the dot-product
     # chain (M*C ciphertexts, L = 3) -- 8 launches per key switch, timed live with CUDA events
     Lk = ctx.top_limbs - 6
@@ -463,12 +469,49 @@ def run_gpu(args):
             "gpu_launches": int(launches) * world,
             "gpu_launches_per_step_per_gpu": int(launches) // args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "keyswitch_ops_per_s": ks_extra, "doubling_mode": fast,
+            "keyswitch_ops_per_s": ks_extra, "doubling_mode": fast, "linear_transform": lt,
             "check": {"max_abs_err_vs_plaintext_lr": err, "tolerance": 1e-3},
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def linear_transform_sharded(torch, eng, client, par, local, rank, world, timed, d=128, log_n=14):
+    """BASELINE config 3 (linear_transformation2.cpp, helper.h:237-262) with the diagonals sharded
+    across the ranks: every rank rotates ct + rot(ct,-d) by ITS diagonals' steps,
+    multiplies by its plaintext diagonals and sums; one all-gather + mod-q add combines the partial
+    ciphertexts.  The combined ciphertext is checked bit-for-bit against the unsharded transform."""
+    wl = importlib.import_module(PKG + ".workloads")
+    params = importlib.import_module(PKG + ".params")
+    ctx = eng.Context(log_n, params.coeff_modulus_create(log_n, [60, 40, 40, 60]), device=local)
+    ev = eng.Evaluator(ctx)
+    enc = client.CKKSEncoder(ctx)
+    kg = client.KeyGenerator(ctx, seed=77)               # same keys and inputs on every rank
+    keys = kg.keyset(steps=[s for i in range(8) for s in (1 << i, -(1 << i))])
+    encr = client.Encryptor(ctx, kg.public_key(), seed=78)
+    decr = client.Decryptor(ctx, kg.secret_key())
+    rng = np.random.default_rng(79)
+    U, v = rng.uniform(0, 1, (d, d)), rng.uniform(0, 1, d)
+    ct = encr.encrypt(enc.encode(v, SCALE))
+    diags = enc.encode(wl.all_diagonals(U), SCALE)
+    plans = wl.PlanCache(ctx, keys)
+    mine = par.shard_units(d, rank, world)
+    idx = torch.tensor(mine, device=ctx.device)
+    diags_local = eng.Ciphertext(ctx, diags.data[idx].contiguous(), diags.limbs, diags.scale)
+
+    def sharded():
+        dup = wl.duplicate_fill(ev, ct, d, keys)
+        return par.sharded_linear_transform_plain(ev, lambda steps: ev.rotate_plan(dup, plans.get(steps)), diags_local, d, mine)
+
+    full = wl.linear_transform_plain(ev, ct, diags, keys, plans)
+    ms, out, _, _, _ = timed(sharded, 3, 20)
+    same = bool(torch.equal(out.data[:, :, : out.limbs], full.data[:, :, : full.limbs]))
+    err = float(np.abs(enc.decode(decr.decrypt(out))[0, :d] - U @ v).max())
+    ks_local = plans.get(mine).keyswitches + 1
+    return {"workload": "Linear_Transform_Plain d=%d, N=%d, {60,40,40,60}, diagonals sharded over %d GPU(s)" % (d, 1 << log_n, world),
+            "ms": ms / 20, "transforms_per_s": 20e3 / ms, "scaling": "strong", "key_switches_per_gpu": int(ks_local),
+            "bit_identical_to_unsharded": same, "max_abs_err_vs_plain": err}
 
 
 def _primes():
@@ -527,6 +570,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the key-switch ops/s sweep")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-lt", action="store_true", help="skip the sharded linear-transform (config 3) leg")
     ap.add_argument("--no-fast", action="store_true", help="skip the informational doubling-mode epoch")
     ap.add_argument("--ncu", action="store_true", help="profiling run: one epoch between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -53,7 +54,8 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("CKKS_NO_PDL") != nullptr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
