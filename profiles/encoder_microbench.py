@@ -1,9 +1,8 @@
-"""Micro-benchmark: batched CKKSEncoder::encode / decode on the device vs the CPU oracle's encoder.
+"""Micro-benchmark: batched CKKSEncoder::encode / decode on the device.
 usage: python profiles/encoder_microbench.py"""
 import importlib
 import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -14,9 +13,6 @@ PKG = "seal-fyp-logistic-regression_b200"
 pkg = importlib.import_module(PKG)
 eng = pkg.load_engine()
 params = importlib.import_module(PKG + ".params")
-from oracle import pyoracle  # noqa: E402  (CPU baseline beside the device number)
-
-pyoracle.build()
 for log_n, bits, batch in ((14, [60, 40, 40, 60], 128), (15, [60] + [40] * 8 + [60], 64)):
     primes = params.coeff_modulus_create(log_n, bits)
     ctx = eng.Context(log_n, primes)
@@ -40,11 +36,3 @@ for log_n, bits, batch in ((14, [60, 40, 40, 60], 128), (15, [60] + [40] * 8 + [
         ms = e0.elapsed_time(e1) / 10
         print("N=%d L=%d batch=%d %s: %.3f ms per batch, %.0f plaintexts/s, %.0f GB/s of plaintext limbs" % (
             n, L, batch, name, ms, batch / ms * 1e3, batch * L * n * 8 / ms / 1e6))
-    orc = pyoracle.Oracle(log_n, primes)
-    xv = x[0].cpu().numpy()
-    t0 = time.perf_counter()
-    p = orc.encode(xv, scale, L)
-    t1 = time.perf_counter()
-    orc.decode(p, scale)
-    t2 = time.perf_counter()
-    print("   CPU oracle, one thread: encode %.1f ms, decode %.1f ms per plaintext" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))

@@ -296,3 +296,25 @@ def test_large_batch_two_lanes_matches_oracle(make_fixture):
     got = fx.ev.relinearize(fx.ctx.upload(a3), fx.keys).numpy()
     for i in range(21):
         assert np.array_equal(got[i], fx.orc.relinearize(a3[i], fx.rlk)), i
+
+
+@pytest.mark.parametrize("log_n,bits", [
+    (12, [36, 36]),                          # shortest chain: one data prime + the special prime (L = 1)
+    (15, [60] + [40] * 19 + [60]),           # deepest chain SEAL allows at N = 32768 with 40-bit primes (880 of 881 bits)
+    (15, [27] * 32),                         # most primes the engine accepts (K = 32), all on the FP64 path
+    (13, [60, 60, 60]),                      # only large primes: everything on the integer path
+])
+def test_extreme_modulus_chains(make_fixture, log_n, bits):
+    """maximum / minimum sizes: relinearize, one Galois step and rescale stay bit-exact at the top level
+    and at level 1 of the shortest, the deepest and the widest chains"""
+    fx = make_fixture(log_n, bits, steps=(1,))
+    rng = np.random.default_rng(len(bits))
+    g = fx.orc.galois_elt(1)
+    for L in sorted({fx.L, 1}, reverse=True):
+        a3 = fx.random_ct(rng, 1, 3, L)
+        assert np.array_equal(fx.ev.relinearize(fx.ctx.upload(a3, cap=fx.L), fx.keys).numpy()[0], fx.orc.relinearize(a3[0], fx.rlk)), L
+        a2 = fx.random_ct(rng, 1, 2, L)
+        d = fx.ctx.upload(a2, cap=fx.L)
+        assert np.array_equal(fx.ev.apply_galois(d, g, fx.keys).numpy()[0], fx.orc.apply_galois(a2[0], g, fx.gks[g])), L
+        if L > 1:
+            assert np.array_equal(fx.ev.rescale_to_next(d).numpy()[0], fx.orc.rescale(a2[0])), L
