@@ -77,7 +77,9 @@ int ckks_ctx_reserve(ckks_ctx *ctx, int batch, int limbs);
 uint64_t ckks_ctx_launch_count(const ckks_ctx *ctx);
 void ckks_ctx_reset_launch_count(ckks_ctx *ctx);
 
-/* ---- memory / stream helpers for hosts that do not bring their own allocator */
+/* ---- memory / stream helpers for hosts that do not bring their own allocator.  Device buffers come
+ * from the stream-ordered memory pool of the device (cudaMallocAsync / cudaFreeAsync on the default
+ * stream, freed memory kept for reuse). */
 int ckks_dev_alloc(ckks_ctx *ctx, size_t bytes, void **out);
 int ckks_dev_free(ckks_ctx *ctx, void *p);
 int ckks_host_alloc(size_t bytes, void **out);   /* pinned */
@@ -199,6 +201,18 @@ int ckks_encode_scalar(ckks_ctx *ctx, double value, double scale, const ckks_vie
  * logistic_regression_ckks.cpp:365,499): `in` is a size-1 view at any level, `values` a DEVICE array
  * [in->batch][N/2] receiving the real parts of the slots.  `in` is not modified. */
 int ckks_decode(ckks_ctx *ctx, const ckks_view *in, double scale, double *values, ckks_stream s);
+
+/* ---- KeyGenerator / Encryptor randomness on the device (tolerance-compared paths only) ------------
+ * util::sample_poly_ternary / sample_poly_normal (sigma 3.2, clipped at 6 sigma) / sample_poly_uniform as
+ * used by KeyGenerator (keygen.secret_key(), public_key(), relin_keys(), galois_keys():
+ * linear_transformation2.cpp:236-239) and Encryptor::encrypt (:347-349).  `out` is a size-1 view of
+ * out->batch polynomials over limbs [0, out->limbs); ternary and normal polynomials hold the same small
+ * integer in every limb and are returned in NTT form, uniform polynomials are independent per limb.
+ * Counter-based generator keyed by `seed`; (`seed`, `stream_id`) must not repeat between calls. */
+#define CKKS_SAMPLE_TERNARY 0
+#define CKKS_SAMPLE_NORMAL 1
+#define CKKS_SAMPLE_UNIFORM 2
+int ckks_sample(ckks_ctx *ctx, int kind, uint64_t seed, uint64_t stream_id, const ckks_view *out, ckks_stream s);
 
 #ifdef __cplusplus
 }

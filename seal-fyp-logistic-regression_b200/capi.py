@@ -89,6 +89,7 @@ SIGNATURES = {
     "ckks_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, _VP, C.c_void_p]),
     "ckks_encode_scalar": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _VP, C.c_void_p]),
     "ckks_decode": (C.c_int, [C.c_void_p, _VP, C.c_double, C.c_void_p, C.c_void_p]),
+    "ckks_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, _VP, C.c_void_p]),
 }
 
 _lib = None

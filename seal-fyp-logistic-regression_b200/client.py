@@ -136,28 +136,24 @@ class _RingOps:
     def __init__(self, ctx, rng):
         self.ctx, self.rng = ctx, rng
         self.ev = Evaluator(ctx)
+        self._seed = int(rng.integers(0, 2 ** 63))
+        self._stream = 0
 
-    def small_to_ntt(self, small, limbs):
-        """signed small integer polys [P][N] -> device tensor [P][limbs][N], NTT form"""
-        res = np.empty((small.shape[0], limbs, self.ctx.n), dtype=np.uint64)
-        for j in range(limbs):
-            res[:, j, :] = np.mod(small, np.int64(self.ctx.primes[j])).astype(np.uint64)
-        t = torch.from_numpy(res.view(np.int64)).to(self.ctx.device)
-        self.ev.ntt_forward(t)
-        return t
+    def _draw(self, kind, count, limbs):
+        """sampling runs on the device (ckks_sample): counter-based generator keyed by this object's seed"""
+        self._stream += 1
+        return self.ev.sample(kind, self._seed, self._stream, count, limbs)
 
-    def ternary(self, count):
-        return self.rng.integers(-1, 2, size=(count, self.ctx.n))
+    def ternary_ntt(self, count, limbs):
+        """count ternary polynomials, the same small integers in every limb, NTT form: [count][limbs][N]"""
+        return self._draw(Evaluator.TERNARY, count, limbs)
 
-    def errors(self, count):
-        e = np.round(self.rng.normal(0.0, 3.2, size=(count, self.ctx.n)))
-        return np.clip(e, -19, 19).astype(np.int64)        # sigma 3.2, clipped at 6 sigma
+    def errors_ntt(self, count, limbs):
+        """rounded normal, sigma 3.2, clipped at 6 sigma (SEAL sample_poly_normal), NTT form"""
+        return self._draw(Evaluator.NORMAL, count, limbs)
 
     def uniform(self, count, limbs):
-        res = np.empty((count, limbs, self.ctx.n), dtype=np.uint64)
-        for j in range(limbs):
-            res[:, j, :] = self.rng.integers(0, self.ctx.primes[j], size=(count, self.ctx.n), dtype=np.uint64)
-        return torch.from_numpy(res.view(np.int64)).to(self.ctx.device)
+        return self._draw(Evaluator.UNIFORM, count, limbs)
 
     def polys(self, t, limbs):
         """[P][limbs][N] tensor -> size-1 Ciphertext batch over primes [0, limbs)"""
@@ -171,7 +167,7 @@ class _RingOps:
     def enc_zero_sym(self, count, sk, limbs):
         """count x (-(a s + e), a) over primes [0, limbs): tensor [count][2][limbs][N]"""
         a = self.uniform(count, limbs)
-        e = self.small_to_ntt(self.errors(count), limbs)
+        e = self.errors_ntt(count, limbs)
         ase = self.ev.add(self.polys(self.mul(a, sk[:limbs]), limbs), self.polys(e, limbs))
         self.ev.negate_inplace(ase)
         return torch.stack([ase.data[:, 0], a], dim=1).contiguous()
@@ -184,7 +180,7 @@ class KeyGenerator:
     def __init__(self, ctx, seed=0):
         self.ctx = ctx
         self.ops = _RingOps(ctx, np.random.default_rng(seed))
-        self._sk = self.ops.small_to_ntt(self.ops.ternary(1), ctx.K)[0]      # [K][N]
+        self._sk = self.ops.ternary_ntt(1, ctx.K)[0]      # [K][N]
 
     def secret_key(self):
         return self._sk
@@ -246,10 +242,10 @@ class Encryptor:
         ctx, ops, ev = self.ctx, self.ops, self.ops.ev
         B, L = pt.batch, pt.limbs
         W = L + 1                      # primes 0..L: prime L is the next data prime or, at the top, P
-        u = ops.small_to_ntt(ops.ternary(B), W)
+        u = ops.ternary_ntt(B, W)
         parts = []
         for k in range(2):
-            e = ops.small_to_ntt(ops.errors(B), W)
+            e = ops.errors_ntt(B, W)
             upk = ops.polys(ops.mul(u, self.pk[k, :W]), W)
             parts.append(ev.add(upk, ops.polys(e, W)).data[:, 0])
         big = Ciphertext(ctx, torch.stack(parts, dim=1).contiguous(), W)

@@ -185,3 +185,69 @@ __global__ void k_dec_gather(const double2 *v, const uint32_t *kidx, double *val
     if (i >= N / 2) return;
     values[(size_t)b * (N / 2) + i] = v[(size_t)b * N + (__brev(kidx[i]) >> (32 - LOGN))].x;
 }
+
+// ------------------------------------------------------------------------------------ sampling
+// KeyGenerator / Encryptor randomness on the device: SEAL's sample_poly_ternary, sample_poly_normal
+// (sigma 3.2, clipped at 6 sigma) and sample_poly_uniform.  Philox4x32-10 keyed by the caller's seed,
+// counter = (coefficient, polynomial, stream id): reproducible and order-independent.  Philox is a
+// statistical generator, not a CSPRNG -- the same holds for the std::mt19937_64 it replaces; a
+// deployment swaps in AES-CTR here.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// kind 0: ternary {-1,0,1}; kind 1: rounded normal, sigma 3.2, |v| <= 19.  The same small integer is
+// reduced into every limb (coefficient form; the caller transforms).
+__global__ void k_sample_small(DView out, int limbs, int n, int kind, u64 seed, u64 stream_id, Tables t) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (j >= n) return;
+    const uint4 r = philox4x32_10(make_uint4((unsigned)j, (unsigned)b, (unsigned)stream_id, (unsigned)(stream_id >> 32)),
+                                  make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    int v;
+    if (kind == 0) {
+        v = (int)(((u64)r.x * 3) >> 32) - 1;
+    } else {
+        const double u1 = ((double)(((u64)r.x << 32) | r.y) + 0.5) * 5.421010862427522e-20;   // (0, 1]
+        const double u2 = ((double)r.z + 0.5) * 2.3283064365386963e-10;
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        const double z = 3.2 * sqrt(-2.0 * log(u1)) * cs;
+        v = (int)rint(fmin(fmax(z, -19.0), 19.0));
+    }
+    u64 *o = out.data + (size_t)b * out.bs + j;
+    for (int l = 0; l < limbs; l++) {
+        const u64 p = t.mod[l].p;
+        o[(size_t)l * n] = v >= 0 ? (u64)v : p - (u64)(-v);
+    }
+}
+
+// uniform residues in [0, q_l) for every limb by Lemire's multiply-shift with rejection: x uniform on
+// 64 bits, result hi64(x * q); draws whose low product word falls below 2^64 mod q are redrawn, which
+// makes the result exactly uniform (rejection probability q / 2^64 < 1/16 per draw).
+__global__ void k_sample_uniform(DView out, int limbs, int n, u64 seed, u64 stream_id, Tables t) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (j >= n) return;
+    u64 *o = out.data + (size_t)b * out.bs + j;
+    for (int l = 0; l < limbs; l++) {
+        const u64 p = t.mod[l].p;
+        const u64 thresh = (0 - p) % p;       // 2^64 mod p
+        u64 res = 0;
+        for (unsigned attempt = 0; attempt < 8; attempt++) {
+            const uint4 r = philox4x32_10(make_uint4((unsigned)j, (unsigned)b | ((unsigned)l << 20) | (attempt << 26),
+                                                     (unsigned)stream_id, (unsigned)(stream_id >> 32)),
+                                          make_uint2((unsigned)seed, ~(unsigned)(seed >> 32)));
+            const u64 x = ((u64)r.x << 32) | r.y;
+            res = __umul64hi(x, p);
+            if (x * p >= thresh) break;        // unbiased draw (rejects with probability p / 2^64 < 1/16)
+        }
+        o[(size_t)l * n] = res;
+    }
+}

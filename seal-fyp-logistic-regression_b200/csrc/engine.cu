@@ -67,6 +67,7 @@ struct ckks_ctx {
     void *d_mod = nullptr, *d_twf = nullptr, *d_twi = nullptr, *d_inv = nullptr, *d_invs = nullptr, *d_half = nullptr;
     void *d_fp = nullptr, *d_twfd = nullptr, *d_twid = nullptr;
     std::unordered_map<uint64_t, uint32_t *> perms;
+    bool pool_ready = false;
     uint32_t *d_kidx = nullptr;                 // encoder: slot i -> DFT position (3^i mod 2N - 1)/2
     std::vector<HalfDigits> half_digits;        // decoder: mixed-radix digits of (Q_L - 1)/2, index L
     u64 *ws = nullptr;
@@ -277,14 +278,28 @@ extern "C" int ckks_ctx_reserve(ckks_ctx *c, int batch, int limbs) {
 }
 
 // ------------------------------------------------------------------------------------ helpers
+// Device buffers for callers without their own allocator (the seal.h shim allocates one per
+// Plaintext / Ciphertext): served from the device's stream-ordered memory pool on the default
+// stream, with the pool told to keep freed memory -- a plain cudaMalloc costs ~2 ms on this part
+// and cudaFree synchronises the device, which dominated the reference's programs.
 extern "C" int ckks_dev_alloc(ckks_ctx *c, size_t bytes, void **out) {
     CU(cudaSetDevice(c->device));
-    if (cudaMalloc(out, bytes) != cudaSuccess) return fail(CKKS_ERR_NOMEM, "device allocation failed");
+    if (!c->pool_ready) {
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, c->device));
+        uint64_t keep = ~0ull;
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        c->pool_ready = true;
+    }
+    if (cudaMallocAsync(out, bytes, (cudaStream_t)0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CKKS_ERR_NOMEM, "device allocation failed");
+    }
     return CKKS_OK;
 }
 extern "C" int ckks_dev_free(ckks_ctx *c, void *p) {
     CU(cudaSetDevice(c->device));
-    CU(cudaFree(p));
+    CU(cudaFreeAsync(p, (cudaStream_t)0));
     return CKKS_OK;
 }
 extern "C" int ckks_host_alloc(size_t bytes, void **out) {
@@ -1193,4 +1208,25 @@ extern "C" int ckks_decode(ckks_ctx *c, const ckks_view *in, double scale, doubl
 #undef RUN
     }
     return CKKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ sampling
+extern "C" int ckks_sample(ckks_ctx *c, int kind, uint64_t seed, uint64_t stream_id, const ckks_view *out, ckks_stream s) {
+    int rc;
+    if ((rc = check_view(c, out, "destination"))) return rc;
+    if (out->size != 1) return fail(CKKS_ERR_INVALID, "sample: destination must have size 1");
+    if (kind < 0 || kind > 2) return fail(CKKS_ERR_INVALID, "sample: unknown distribution");
+    if (out->batch > 1 && out->batch_stride == 0) return fail(CKKS_ERR_INVALID, "sample: destination entries must be distinct");
+    if (out->batch >= (1 << 20)) return fail(CKKS_ERR_INVALID, "sample: batch too large");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)s;
+    const dim3 grid((c->n + 255) / 256, out->batch);
+    if (kind == 2) {
+        k_sample_uniform<<<grid, 256, 0, st>>>(dv(out), out->limbs, c->n, seed, stream_id, c->t);
+        LAUNCH_CHECK(c);
+        return CKKS_OK;   // uniform in the NTT domain is uniform
+    }
+    k_sample_small<<<grid, 256, 0, st>>>(dv(out), out->limbs, c->n, kind, seed, stream_id, c->t);
+    LAUNCH_CHECK(c);
+    return ntt_api(c, (uint64_t *)out->data, out->batch, out->limbs, 0, out->batch > 1 ? out->batch_stride : out->poly_stride, false, st);
 }

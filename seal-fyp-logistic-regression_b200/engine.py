@@ -409,6 +409,17 @@ class Evaluator:
         check(self.lib.ckks_decode(self.h, C.byref(vi), float(pt.scale), out.data_ptr(), _stream()))
         return out
 
+    # ---- KeyGenerator / Encryptor randomness on the device (ckks_sample)
+    TERNARY, NORMAL, UNIFORM = 0, 1, 2
+
+    def sample(self, kind, seed, stream_id, count, limbs):
+        """count polynomials over primes [0, limbs) -> int64 CUDA tensor [count][limbs][N]; ternary and
+        normal (sigma 3.2, clipped) polynomials come back in NTT form"""
+        out = self.ctx.empty(count, 1, limbs)
+        vo = out.view()
+        check(self.lib.ckks_sample(self.h, int(kind), int(seed) & (2 ** 64 - 1), int(stream_id), C.byref(vo), _stream()))
+        return out.data[:, 0]
+
     # ---- raw NTT (tests / encoder)
     def ntt_forward(self, tensor, first_prime=0):
         """tensor: [P][L][N] int64, limb l uses prime first_prime + l; in place"""

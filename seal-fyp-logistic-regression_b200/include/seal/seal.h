@@ -443,10 +443,15 @@ public:
 namespace detail {
 
 // thin wrappers: every ring operation goes through the GPU engine
+inline std::uint64_t fresh_seed() {
+    std::random_device rd;
+    return ((std::uint64_t)rd() << 32) ^ (std::uint64_t)rd();
+}
+
 struct Ring {
     std::shared_ptr<Engine> e;
-    std::mt19937_64 rng;
-    explicit Ring(std::shared_ptr<Engine> eng, std::uint64_t seed) : e(std::move(eng)), rng(seed) {}
+    std::uint64_t seed_, stream_ = 0;
+    explicit Ring(std::shared_ptr<Engine> eng, std::uint64_t seed) : e(std::move(eng)), seed_(seed) {}
 
     ckks_view view(std::uint64_t *p, int batch, int size, int limbs) const {
         ckks_view v;
@@ -459,59 +464,23 @@ struct Ring {
         v.reserved = 0;
         return v;
     }
-    // small signed polynomials [count][N] -> device [count][limbs][N] in NTT form
-    BufPtr small_to_ntt(const std::vector<int> &small, int count, int limbs) {
-        std::size_t n = e->n;
-        std::vector<std::uint64_t> h((std::size_t)count * limbs * n);
-        for (int c = 0; c < count; c++)
-            for (int j = 0; j < limbs; j++) {
-                std::uint64_t p = e->primes[j];
-                for (std::size_t q = 0; q < n; q++) {
-                    int v = small[(std::size_t)c * n + q];
-                    h[((std::size_t)c * limbs + j) * n + q] = v >= 0 ? (std::uint64_t)v : p - (std::uint64_t)(-v);
-                }
-            }
-        auto b = std::make_shared<DevBuf>(e, h.size());
-        check(ckks_upload(e->ctx, b->p, h.data(), h.size() * 8, nullptr));
-        check(ckks_stream_sync(e->ctx, nullptr));   // h goes out of scope
-        check(ckks_ntt_forward(e->ctx, b->p, count, limbs, 0, (std::uint64_t)limbs * n, nullptr));
+    // Sampling runs on the device (ckks_sample): a counter-based generator keyed by this object's
+    // seed, one stream id per call.  count polynomials over primes [0, limbs): device [count][limbs][N];
+    // ternary and normal polynomials hold the same small integer in every limb and come back in NTT form.
+    BufPtr draw(int kind, int count, int limbs) {
+        auto b = std::make_shared<DevBuf>(e, (std::size_t)count * limbs * e->n);
+        ckks_view v = view(b->p, count, 1, limbs);
+        check(ckks_sample(e->ctx, kind, seed_, ++stream_, &v, nullptr));
         return b;
     }
-    std::vector<int> ternary(int count) {
-        std::vector<int> v((std::size_t)count * e->n);
-        std::uniform_int_distribution<int> d(-1, 1);
-        for (auto &x : v) x = d(rng);
-        return v;
-    }
-    std::vector<int> errors(int count) {   // sigma 3.2, clipped at 6 sigma (SEAL sample_poly_normal)
-        std::vector<int> v((std::size_t)count * e->n);
-        std::normal_distribution<double> d(0.0, 3.2);
-        for (auto &x : v) {
-            double z;
-            do z = d(rng);
-            while (std::fabs(z) > 19.2);
-            x = (int)std::lround(z);
-        }
-        return v;
-    }
-    BufPtr uniform(int count, int limbs) {
-        std::size_t n = e->n;
-        std::vector<std::uint64_t> h((std::size_t)count * limbs * n);
-        for (int c = 0; c < count; c++)
-            for (int j = 0; j < limbs; j++) {
-                std::uniform_int_distribution<std::uint64_t> d(0, e->primes[j] - 1);
-                for (std::size_t q = 0; q < n; q++) h[((std::size_t)c * limbs + j) * n + q] = d(rng);
-            }
-        auto b = std::make_shared<DevBuf>(e, h.size());
-        check(ckks_upload(e->ctx, b->p, h.data(), h.size() * 8, nullptr));
-        check(ckks_stream_sync(e->ctx, nullptr));
-        return b;
-    }
+    BufPtr ternary_ntt(int count, int limbs) { return draw(CKKS_SAMPLE_TERNARY, count, limbs); }
+    BufPtr errors_ntt(int count, int limbs) { return draw(CKKS_SAMPLE_NORMAL, count, limbs); }   // sigma 3.2, clipped at 6 sigma
+    BufPtr uniform(int count, int limbs) { return draw(CKKS_SAMPLE_UNIFORM, count, limbs); }
     // count x (-(a s + e), a) over primes [0, limbs): device [count][2][limbs][N]
     BufPtr enc_zero_sym(int count, const std::uint64_t *sk, int limbs) {
         std::size_t n = e->n, pw = (std::size_t)limbs * n;
         auto a = uniform(count, limbs);
-        auto err = small_to_ntt(errors(count), count, limbs);
+        auto err = errors_ntt(count, limbs);
         auto out = std::make_shared<DevBuf>(e, (std::size_t)count * 2 * pw);
         auto tmp = std::make_shared<DevBuf>(e, (std::size_t)count * pw);
         ckks_view va = view(a->p, count, 1, limbs), vs = view(const_cast<std::uint64_t *>(sk), 1, 1, limbs);
@@ -534,9 +503,9 @@ struct Ring {
 class KeyGenerator {
 public:
     template <class Ctx>
-    explicit KeyGenerator(const Ctx &context) : ring_(detail::engine_of(context), std::random_device{}()) {
+    explicit KeyGenerator(const Ctx &context) : ring_(detail::engine_of(context), detail::fresh_seed()) {
         auto &e = ring_.e;
-        sk_.buf = ring_.small_to_ntt(ring_.ternary(1), 1, e->K);
+        sk_.buf = ring_.ternary_ntt(1, e->K);
     }
     const SecretKey &secret_key() const { return sk_; }
     PublicKey public_key() {
@@ -723,7 +692,7 @@ private:
 class Encryptor {
 public:
     template <class Ctx>
-    Encryptor(const Ctx &context, const PublicKey &pk) : ring_(detail::engine_of(context), std::random_device{}()), pk_(pk) {}
+    Encryptor(const Ctx &context, const PublicKey &pk) : ring_(detail::engine_of(context), detail::fresh_seed()), pk_(pk) {}
 
     // (u pk + e) one level above the plaintext's level, divided-and-rounded by the extra prime
     // (the rescale kernels), plus the plaintext in c0
@@ -733,10 +702,10 @@ public:
         if (!pt.buf) throw std::invalid_argument("plain is not valid for encryption parameters");
         std::size_t n = e->n;
         int L = pt.limbs, W = L + 1, K = e->K;
-        auto u = ring_.small_to_ntt(ring_.ternary(1), 1, W);
+        auto u = ring_.ternary_ntt(1, W);
         auto big = std::make_shared<detail::DevBuf>(e, (std::size_t)2 * W * n);
         for (int k = 0; k < 2; k++) {
-            auto err = ring_.small_to_ntt(ring_.errors(1), 1, W);
+            auto err = ring_.errors_ntt(1, W);
             ckks_view vu = ring_.view(u->p, 1, 1, W), ve = ring_.view(err->p, 1, 1, W);
             ckks_view vpk = ring_.view(pk_.buf->p + (std::size_t)k * K * n, 1, 1, W);
             ckks_view vo = ring_.view(big->p + (std::size_t)k * W * n, 1, 1, W);

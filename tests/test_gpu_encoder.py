@@ -121,3 +121,35 @@ def test_encoder_errors(make_fixture):
     # an empty value vector encodes the zero plaintext (SEAL accepts it)
     z = fx.ev.encode(torch.zeros((1, 0), dtype=torch.float64), 2.0 ** 30)
     assert not z.numpy().any()
+
+
+def test_device_sampler_distributions(make_fixture):
+    """ckks_sample: ternary / clipped normal / uniform polynomials drawn on the device.
+    Statistical checks (the generator is not SEAL's, outputs are compared by distribution), exact checks
+    for structure: the same small integer in every limb, range, determinism per (seed, stream)."""
+    fx = make_fixture(13, [60, 40, 40, 60], steps=(1,))
+    ev, n, K = fx.ev, fx.ctx.n, len(fx.primes)
+
+    def small(kind, seed, stream, count=4):
+        t = ev.sample(kind, seed, stream, count, K).cpu().numpy().view(np.uint64)
+        cent = np.stack([[_centered(fx.orc.intt(j, t[b, j]), fx.primes[j]) for j in range(K)] for b in range(count)])
+        assert all(np.array_equal(cent[:, 0], cent[:, j]) for j in range(1, K))      # one integer, K residues
+        return cent[:, 0]
+
+    tern = small(ev.TERNARY, 1234, 1)
+    assert set(np.unique(tern)) == {-1, 0, 1}
+    for v in (-1, 0, 1):
+        assert abs((tern == v).mean() - 1 / 3) < 0.01
+    err = small(ev.NORMAL, 1234, 2)
+    assert np.abs(err).max() <= 19
+    assert abs(err.mean()) < 0.1 and abs(err.std() - np.sqrt(3.2 ** 2 + 1 / 12)) < 0.1
+    assert np.array_equal(small(ev.NORMAL, 1234, 2), err)                            # reproducible
+    assert not np.array_equal(small(ev.NORMAL, 1234, 3), err)                        # new stream, new draw
+    assert not np.array_equal(small(ev.NORMAL, 1235, 2), err)                        # new seed, new draw
+    assert not np.array_equal(err[0], err[1])                                        # polynomials differ
+    uni = ev.sample(ev.UNIFORM, 99, 7, 8, K).cpu().numpy().view(np.uint64)
+    for j, p in enumerate(fx.primes):
+        assert uni[:, j].max() < p
+        assert abs(uni[:, j].astype(np.float64).mean() / p - 0.5) < 0.01
+        assert abs(uni[:, j].astype(np.float64).std() / p - np.sqrt(1 / 12)) < 0.01
+    assert not np.array_equal(uni[:, 1] % 1000003, uni[:, 2] % 1000003)              # limbs are independent
