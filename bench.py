@@ -505,13 +505,21 @@ def linear_transform_sharded(torch, eng, client, par, local, rank, world, timed,
         return par.sharded_linear_transform_plain(ev, lambda steps: ev.rotate_plan(dup, plans.get(steps)), diags_local, d, mine)
 
     full = wl.linear_transform_plain(ev, ct, diags, keys, plans)
+    bsgs = None
+    if world == 1:   # SURVEY 8(f4) mode beside it: baby-step / giant-step, tolerance-checked, not the reference sequence
+        bd = wl.BsgsDiagonals(U, SCALE, enc, baby=16)
+        ms_b, out_b, _, _, _ = timed(lambda: wl.linear_transform_plain_bsgs(ev, ct, bd, keys, plans), 3, 20)
+        bsgs = {"ms": ms_b / 20, "baby": bd.b, "giant": bd.G,
+                "key_switches": int(plans.get(range(bd.b)).keyswitches + plans.get([g * bd.b for g in range(bd.G)]).keyswitches + 1),
+                "max_abs_err_vs_plain": float(np.abs(enc.decode(decr.decrypt(out_b))[0, :d] - U @ v).max()),
+                "note": "not the reference's op sequence; ciphertexts differ, decrypted result agrees"}
     ms, out, _, _, _ = timed(sharded, 3, 20)
     same = bool(torch.equal(out.data[:, :, : out.limbs], full.data[:, :, : full.limbs]))
     err = float(np.abs(enc.decode(decr.decrypt(out))[0, :d] - U @ v).max())
     ks_local = plans.get(mine).keyswitches + 1
     return {"workload": "Linear_Transform_Plain d=%d, N=%d, {60,40,40,60}, diagonals sharded over %d GPU(s)" % (d, 1 << log_n, world),
             "ms": ms / 20, "transforms_per_s": 20e3 / ms, "scaling": "strong", "key_switches_per_gpu": int(ks_local),
-            "bit_identical_to_unsharded": same, "max_abs_err_vs_plain": err}
+            "bit_identical_to_unsharded": same, "max_abs_err_vs_plain": err, "bsgs_mode": bsgs}
 
 
 def _primes():

@@ -63,6 +63,41 @@ def linear_transform_cipher(ev, ct, diag_cts, keys, plans):
     return ev.multiply_sum(rots, diag_cts)
 
 
+class BsgsDiagonals:
+    """the d diagonals of a transform, pre-rotated for the baby-step / giant-step evaluation
+    (SURVEY 8(f4)): diagonal l = g*b + s is encoded with its entries moved to slots [g*b, g*b + d)."""
+
+    def __init__(self, U, scale, encoder, baby=None, limbs=None):
+        d = U.shape[0]
+        self.d = d
+        self.b = int(baby) if baby else max(1, int(round(math.sqrt(d))))
+        self.G = (d + self.b - 1) // self.b
+        diags = all_diagonals(U)
+        vals = np.zeros((d, 2 * d))
+        for l in range(d):
+            off = (l // self.b) * self.b
+            vals[l, off:off + d] = diags[l]
+        self.plain = encoder.encode(vals, scale, limbs=limbs)      # batch d, entry l
+
+
+def linear_transform_plain_bsgs(ev, ct, bd, keys, plans):
+    """Linear_Transform_Plain by baby steps and giant steps -- an explicit,
+    tolerance-checked alternative to linear_transform_plain, never the default:
+        sum_g rot( sum_s rot(diag_{gb+s}, -gb) (.) rot(ct + rot(ct,-d), s), gb )
+    b + G - 2 composite rotations instead of d - 1; the decrypted result equals the reference
+    sequence within noise, the ciphertext polynomials do not."""
+    d, b, G = bd.d, bd.b, bd.G
+    dup = duplicate_fill(ev, ct, d, keys)
+    baby = ev.rotate_plan(dup, plans.get(range(b)))                # batch b: rot(dup, s)
+    inner = []
+    for g in range(G):
+        lo, hi = g * b, min(d, (g + 1) * b)
+        pts = Ciphertext(bd.plain.ctx, bd.plain.data[lo:hi], bd.plain.limbs, bd.plain.scale)
+        inner.append(ev.multiply_plain_sum(baby[0:hi - lo], pts))
+    giant = ev.rotate_plan(_stack(inner), plans.get([g * b for g in range(G)]))
+    return ev.add_many(giant)
+
+
 def linear_transform_ciphermatrix_plainvector(ev, pt_rotations, ct_diags):
     """Linear_Transform_CipherMatrix_PlainVector (helper.h:265-278)"""
     return ev.multiply_plain_sum(ct_diags, pt_rotations)

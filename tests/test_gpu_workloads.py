@@ -98,6 +98,31 @@ def test_linear_transform_plain_and_cipher(fx12):
     assert np.abs(dec - U @ v).max() < 1e-4
 
 
+def test_linear_transform_bsgs_mode(fx12):
+    """baby-step / giant-step evaluation of Linear_Transform_Plain -- different ciphertext
+    polynomials, same decrypted vector as the reference sequence (and as U @ v), far fewer key switches"""
+    wl, _, client = _mods()
+    fx = fx12
+    plans = wl.PlanCache(fx.ctx, fx.keys)
+    enc = client.CKKSEncoder(fx.ctx)
+    rng = np.random.default_rng(12)
+    scale = 2.0 ** 40
+    for d, baby in ((5, None), (13, 4), (32, None), (64, 8)):
+        U, v = rng.uniform(0, 1, (d, d)), rng.uniform(0, 1, d)
+        ct = fx.ctx.upload(_enc(fx, 300 + d, v, scale), scale=scale)
+        ref = wl.linear_transform_plain(fx.ev, ct, enc.encode(wl.all_diagonals(U), scale), fx.keys, plans)
+        bd = wl.BsgsDiagonals(U, scale, enc, baby=baby)
+        got = wl.linear_transform_plain_bsgs(fx.ev, ct, bd, fx.keys, plans)
+        assert got.limbs == ref.limbs and got.scale == ref.scale
+        assert not np.array_equal(got.numpy(), ref.numpy())
+        dg = fx.orc.decode(fx.orc.decrypt(fx.sk, got.numpy()[0]), got.scale)[:d]
+        dr = fx.orc.decode(fx.orc.decrypt(fx.sk, ref.numpy()[0]), ref.scale)[:d]
+        assert np.abs(dg - dr).max() < 1e-5 and np.abs(dg - U @ v).max() < 1e-4, d
+        ks_ref = plans.get(range(d)).keyswitches
+        ks_bsgs = plans.get(range(bd.b)).keyswitches + plans.get([g * bd.b for g in range(bd.G)]).keyswitches
+        assert ks_bsgs < ks_ref or d <= 5
+
+
 def test_matrix_encode_and_multiplication(make_fixture):
     wl, _, _ = _mods()
     fx = make_fixture(12, [50, 40, 40, 40, 40, 50], steps=POW2)
