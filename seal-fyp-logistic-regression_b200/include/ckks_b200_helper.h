@@ -1,0 +1,229 @@
+// ckks_b200_helper.h -- batched drop-ins for the rotation-heavy functions of the reference's helper.h.
+//
+// Same names, argument order and results as the reference's functions, in namespace b200, built on the
+// batched entry points of include/ckks_b200.h (rotation plans, fused multiply + add_many, the fused
+// rotate-and-sum chain) instead of one evaluator call per ciphertext.  Every function issues, per
+// ciphertext, exactly the reference's evaluator sequence, so the returned ciphertext polynomials are
+// bit-identical to what the reference's own function returns through seal/seal.h (checked by
+// tests/cpp/helper_driver.cpp); what changes is that independent ciphertexts share kernel launches.
+//
+//   reference (helper.h)                               here
+//   Linear_Transform_Plain            :237-262         b200::Linear_Transform_Plain
+//   Linear_Transform_Cipher           :212-234         b200::Linear_Transform_Cipher
+//   Linear_Transform_CipherMatrix_PlainVector :265-278 b200::Linear_Transform_CipherMatrix_PlainVector
+//   C_Matrix_Encode                   :307-322         b200::C_Matrix_Encode
+//   cipher_dot_product                :416-502         b200::cipher_dot_product
+//
+// A maintainer switches a call site by prefixing it with b200:: (or `using b200::Linear_Transform_Plain;`).
+// Differences from the reference, all deliberate: arguments are taken by const reference (the reference
+// copies them by value, which is only cheaper here); a zero plaintext diagonal does not raise SEAL's
+// "result ciphertext is transparent" (the reference's drivers add an epsilon to avoid it).
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <vector>
+
+#include "seal/seal.h"
+
+namespace b200 {
+namespace detail {
+
+using seal::detail::BufPtr;
+using seal::detail::check;
+using seal::detail::DevBuf;
+using seal::detail::Engine;
+using seal::detail::Poly;
+
+// B objects of `size` polynomials with `limbs` limbs each, contiguous: [B][size][limbs][N]
+struct Batch {
+    std::shared_ptr<Engine> e;
+    BufPtr buf;
+    int batch = 0, size = 0, limbs = 0;
+    double scale = 1.0;
+    Batch(std::shared_ptr<Engine> eng, int batch_, int size_, int limbs_, double scale_)
+        : e(std::move(eng)), batch(batch_), size(size_), limbs(limbs_), scale(scale_) {
+        buf = std::make_shared<DevBuf>(e, (std::size_t)batch * size * limbs * e->n);
+    }
+    std::size_t entry_words() const { return (std::size_t)size * limbs * e->n; }
+    ckks_view view() const {
+        ckks_view v;
+        v.data = buf->p;
+        v.batch_stride = entry_words();
+        v.poly_stride = (std::uint64_t)limbs * e->n;
+        v.batch = batch;
+        v.size = size;
+        v.limbs = limbs;
+        v.reserved = 0;
+        return v;
+    }
+    // copy one shim object into / out of entry b (limb capacity of the object may exceed its level)
+    void put(int b, const Poly &p) {
+        if (!p.buf || p.size != size || p.limbs != limbs) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+        for (int k = 0; k < size; k++)
+            check(ckks_copy(e->ctx, buf->p + b * entry_words() + (std::size_t)k * limbs * e->n,
+                            p.buf->p + (std::size_t)k * p.cap * e->n, (std::size_t)limbs * e->n * 8, nullptr));
+    }
+    void get(int b, Poly &p) const {
+        p.allocate(e, size, limbs);
+        p.scale = scale;
+        check(ckks_copy(e->ctx, p.buf->p, buf->p + b * entry_words(), entry_words() * 8, nullptr));
+    }
+};
+
+template <class T>
+inline Batch gather(const std::vector<T> &objs) {
+    if (objs.empty()) throw std::invalid_argument("encrypteds cannot be empty");
+    const Poly &p0 = objs[0].poly();
+    if (!p0.buf) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    Batch b(p0.eng, (int)objs.size(), p0.size, p0.limbs, p0.scale);
+    for (std::size_t i = 0; i < objs.size(); i++) {
+        if (objs[i].poly().scale != p0.scale) throw std::invalid_argument("scale mismatch");
+        b.put((int)i, objs[i].poly());
+    }
+    return b;
+}
+
+struct Plan {   // RAII around ckks_rotplan
+    ckks_rotplan *p = nullptr;
+    Plan(const std::shared_ptr<Engine> &e, const seal::GaloisKeys &gk, const std::vector<int> &steps) {
+        if (!gk.s || !gk.s->ks) throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+        check(ckks_rotplan_create(e->ctx, gk.s->ks, steps.data(), (int)steps.size(), &p));
+    }
+    ~Plan() {
+        if (p) ckks_rotplan_destroy(p);
+    }
+    Plan(const Plan &) = delete;
+};
+
+// rot(ct, steps[b]) for every b as one batched call; `in` is one ciphertext (batch 1) or a batch
+inline Batch rotate_all(const ckks_view &in, const std::shared_ptr<Engine> &e, double scale, const seal::GaloisKeys &gk,
+                        const std::vector<int> &steps) {
+    Plan plan(e, gk, steps);
+    Batch out(e, (int)steps.size(), 2, in.limbs, scale), scratch(e, (int)steps.size(), 2, in.limbs, scale);
+    ckks_view vo = out.view(), vs = scratch.view();
+    check(ckks_rotate_plan(e->ctx, plan.p, &in, &vo, &vs, nullptr));
+    return out;
+}
+
+inline void scale_ok(const Engine &e, double scale, int limbs) {
+    long double lg = 0;
+    for (int j = 0; j < limbs; j++) lg += std::log2((long double)e.primes[j]);
+    if (scale <= 0 || (int)std::log2(scale) >= (int)std::floor(lg) + 1) throw std::invalid_argument("scale out of bounds");
+}
+
+// ct + rotate_vector(ct, -d): "Fill ct with duplicate" (helper.h:241-247)
+inline seal::Ciphertext duplicate(const seal::Ciphertext &ct, int d, const seal::GaloisKeys &gk, seal::Evaluator &ev) {
+    seal::Ciphertext rot, out;
+    ev.rotate_vector(ct, -d, gk, rot);
+    ev.add(ct, rot, out);
+    return out;
+}
+
+}  // namespace detail
+
+// helper.h:237-262 -- sum_l U_diagonals[l] (.) rotate_vector(ct + rotate_vector(ct, -d), l)
+inline seal::Ciphertext Linear_Transform_Plain(const seal::Ciphertext &ct, const std::vector<seal::Plaintext> &U_diagonals,
+                                               const seal::GaloisKeys &gal_keys, const seal::EncryptionParameters &params) {
+    auto context = seal::SEALContext::Create(params);
+    seal::Evaluator evaluator(context);
+    const int d = (int)U_diagonals.size();
+    detail::Batch diags = detail::gather(U_diagonals);
+    seal::Ciphertext ct_new = detail::duplicate(ct, d, gal_keys, evaluator);
+    const detail::Poly &pn = ct_new.poly();
+    if (pn.limbs != diags.limbs) throw std::invalid_argument("encrypted and plain parameter mismatch");
+    detail::scale_ok(*pn.eng, pn.scale * diags.scale, pn.limbs);
+    std::vector<int> steps(d);
+    for (int l = 0; l < d; l++) steps[l] = l;
+    detail::Batch rots = detail::rotate_all(pn.view(), pn.eng, pn.scale, gal_keys, steps);
+    seal::Ciphertext out;
+    out.poly().allocate(pn.eng, 2, pn.limbs);
+    out.poly().scale = pn.scale * diags.scale;
+    ckks_view vr = rots.view(), vd = diags.view(), vo = out.poly().view();
+    detail::check(ckks_multiply_plain_sum(pn.eng->ctx, &vr, &vd, &vo, nullptr));
+    return out;
+}
+
+// helper.h:212-234 -- the same with ciphertext diagonals; the result has size 3 (no relinearisation)
+inline seal::Ciphertext Linear_Transform_Cipher(const seal::Ciphertext &ct, const std::vector<seal::Ciphertext> &U_diagonals,
+                                                const seal::GaloisKeys &gal_keys, seal::Evaluator &evaluator) {
+    const int d = (int)U_diagonals.size();
+    detail::Batch diags = detail::gather(U_diagonals);
+    if (diags.size != 2) throw std::invalid_argument("encrypted size must be 2");
+    seal::Ciphertext ct_new = detail::duplicate(ct, d, gal_keys, evaluator);
+    const detail::Poly &pn = ct_new.poly();
+    if (pn.limbs != diags.limbs) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+    detail::scale_ok(*pn.eng, pn.scale * diags.scale, pn.limbs);
+    std::vector<int> steps(d);
+    for (int l = 0; l < d; l++) steps[l] = l;
+    detail::Batch rots = detail::rotate_all(pn.view(), pn.eng, pn.scale, gal_keys, steps);
+    seal::Ciphertext out;
+    out.poly().allocate(pn.eng, 3, pn.limbs);
+    out.poly().scale = pn.scale * diags.scale;
+    ckks_view vr = rots.view(), vd = diags.view(), vo = out.poly().view();
+    detail::check(ckks_multiply_sum(pn.eng->ctx, &vr, &vd, &vo, nullptr));
+    return out;
+}
+
+// helper.h:265-278 -- sum_i U_diagonals[i] (.) pt_rotations[i] (no rotations: the vector is in the clear)
+inline seal::Ciphertext Linear_Transform_CipherMatrix_PlainVector(const std::vector<seal::Plaintext> &pt_rotations,
+                                                                  const std::vector<seal::Ciphertext> &U_diagonals,
+                                                                  const seal::GaloisKeys &, seal::Evaluator &) {
+    if (pt_rotations.size() != U_diagonals.size()) throw std::invalid_argument("encrypted and plain parameter mismatch");
+    detail::Batch cts = detail::gather(U_diagonals), pts = detail::gather(pt_rotations);
+    if (cts.limbs != pts.limbs) throw std::invalid_argument("encrypted and plain parameter mismatch");
+    detail::scale_ok(*cts.e, cts.scale * pts.scale, cts.limbs);
+    seal::Ciphertext out;
+    out.poly().allocate(cts.e, cts.size, cts.limbs);
+    out.poly().scale = cts.scale * pts.scale;
+    ckks_view vc = cts.view(), vp = pts.view(), vo = out.poly().view();
+    detail::check(ckks_multiply_plain_sum(cts.e->ctx, &vc, &vp, &vo, nullptr));
+    return out;
+}
+
+// helper.h:307-322 -- pack the d row ciphertexts of a matrix into one: sum_i rotate_vector(matrix[i], -i*d)
+inline seal::Ciphertext C_Matrix_Encode(const std::vector<seal::Ciphertext> &matrix, const seal::GaloisKeys &gal_keys,
+                                        seal::Evaluator &) {
+    const int d = (int)matrix.size();
+    detail::Batch rows = detail::gather(matrix);
+    if (rows.size != 2) throw std::invalid_argument("encrypted size must be 2");
+    std::vector<int> steps(d);
+    for (int i = 0; i < d; i++) steps[i] = -(i * d);
+    detail::Batch rot = detail::rotate_all(rows.view(), rows.e, rows.scale, gal_keys, steps);
+    seal::Ciphertext out;
+    out.poly().allocate(rows.e, 2, rows.limbs);
+    out.poly().scale = rows.scale;
+    ckks_view vr = rot.view(), vo = out.poly().view();
+    detail::check(ckks_add_many(rows.e->ctx, &vr, &vo, nullptr));
+    return out;
+}
+
+// helper.h:416-502 -- multiply, relinearize, rescale, then the rotate-and-sum loop over `size` slots
+// (size-1 dependent unit rotations, each fused with its add and replayed from a CUDA graph), scale forced
+// to a power of two as the reference does
+inline seal::Ciphertext cipher_dot_product(const seal::Ciphertext &ctA, const seal::Ciphertext &ctB, int size,
+                                           const seal::RelinKeys &relin_keys, const seal::GaloisKeys &gal_keys,
+                                           seal::Evaluator &evaluator) {
+    seal::Ciphertext mult;
+    evaluator.multiply(ctA, ctB, mult);
+    evaluator.relinearize_inplace(mult, relin_keys);
+    evaluator.rescale_to_next_inplace(mult);
+    seal::Ciphertext zero_filled, dup;
+    evaluator.rotate_vector(mult, -size, gal_keys, zero_filled);
+    evaluator.add(mult, zero_filled, dup);
+    if (size > 1) {
+        if (!gal_keys.s || !gal_keys.s->ks) throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+        mult.poly().make_unique();
+        dup.poly().make_unique();
+        detail::Poly &pm = mult.poly(), &pd = dup.poly();
+        detail::Poly scratch;
+        scratch.allocate(pm.eng, 2, pd.limbs);
+        ckks_view va = pd.view(), vb = scratch.view(), vc = pm.view();
+        vb.limbs = va.limbs;
+        int final_in_b = 0;
+        detail::check(ckks_rotate_sum_chain(pm.eng->ctx, gal_keys.s->ks, &va, &vb, &vc, 1, size - 1, &final_in_b, nullptr));
+    }
+    mult.scale() = std::pow(2.0, (int)std::log2(mult.scale()));
+    return mult;
+}
+
+}  // namespace b200

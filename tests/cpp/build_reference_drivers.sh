@@ -14,3 +14,7 @@ for f in 4_ckks matrix_mult_benchmark matrix_multiplication linear_transformatio
       "$PKG/libckks_b200.so" -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../../../seal-fyp-logistic-regression_b200'
   echo "built $f"
 done
+# the reference's helper.h functions vs the batched b200:: drop-ins (bit-identity driver)
+g++ -std=c++17 -O2 -w -I "$ROOT/include" -I "$PKG/include" -I "$REF" "$ROOT/tests/cpp/helper_driver.cpp" -o "$OUT/helper_driver" \
+    "$PKG/libckks_b200.so" -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../../../seal-fyp-logistic-regression_b200'
+echo "built helper_driver"
