@@ -544,6 +544,7 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         JjList &dst = (c->primes[pj] >> 41) == 0 ? small : big;
         dst.jj[dst.n++] = (signed char)jj;
     }
+    const bool special_small = (c->primes[K - 1] >> 41) == 0;
     for (int b0 = slot0; b0 < slot0 + nslots; b0 += Bc) {
         const int bc = (slot0 + nslots - b0) < Bc ? (slot0 + nslots - b0) : Bc;
         rt.b0 = b0;
@@ -581,13 +582,15 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
             else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, c->t);         \
             LAUNCH_CHECK(c);                                                                                            \
         }                                                                                                               \
+        /* a small special prime puts its limb on the side stream: the INTT below must wait for it */            \
+        if (sfp != st && special_small) CU(cudaStreamWaitEvent(st, ln.join, 0));                                        \
         launch_pdl(k_inv_row<LN>, dim3(G::ROW_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);               \
         LAUNCH_CHECK(c);                                                                                                \
         launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);         \
         LAUNCH_CHECK(c);                                                                                                \
         launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, L, 2 * bc), st, spec, T2, L, K - 1, c->t);              \
         LAUNCH_CHECK(c);                                                                                                \
-        if (sfp != st) CU(cudaStreamWaitEvent(st, ln.join, 0));                                                         \
+        if (sfp != st && !special_small) CU(cudaStreamWaitEvent(st, ln.join, 0));                                       \
         if (mode == 2) launch_pdl(k_md_fwd_row<LN, 2>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
         else launch_pdl(k_md_fwd_row<LN, 1>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
         LAUNCH_CHECK(c);                                                                                                \

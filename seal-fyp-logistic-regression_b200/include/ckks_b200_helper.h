@@ -13,6 +13,7 @@
 //   Linear_Transform_CipherMatrix_PlainVector :265-278 b200::Linear_Transform_CipherMatrix_PlainVector
 //   C_Matrix_Encode                   :307-322         b200::C_Matrix_Encode
 //   cipher_dot_product                :416-502         b200::cipher_dot_product
+//   CC_Matrix_Multiplication (matrix_mult_benchmark.cpp:13-71)  b200::CC_Matrix_Multiplication
 //
 // A maintainer switches a call site by prefixing it with b200:: (or `using b200::Linear_Transform_Plain;`).
 // Differences from the reference, all deliberate: arguments are taken by const reference (the reference
@@ -224,6 +225,65 @@ inline seal::Ciphertext cipher_dot_product(const seal::Ciphertext &ctA, const se
     }
     mult.scale() = std::pow(2.0, (int)std::log2(mult.scale()));
     return mult;
+}
+
+// matrix_multiplication.cpp:11-132 / matrix_mult_benchmark.cpp:13-71 -- encrypted d x d matrix product of
+// eprint 2018/1041: sigma(A), tau(B), the d-1 column / row shifts V_k, W_k of them, and sum_k A_k (.) B_k.
+// Every V_k (W_k) transform of the reference rotates the same ciphertext by the same d*d steps; here those
+// rotations are computed once and shared, which leaves every ciphertext polynomial unchanged.
+inline seal::Ciphertext CC_Matrix_Multiplication(const seal::Ciphertext &ctA, const seal::Ciphertext &ctB, int dimension,
+                                                 const std::vector<seal::Plaintext> &U_sigma_diagonals,
+                                                 const std::vector<seal::Plaintext> &U_tau_diagonals,
+                                                 const std::vector<std::vector<seal::Plaintext>> &V_diagonals,
+                                                 const std::vector<std::vector<seal::Plaintext>> &W_diagonals,
+                                                 const seal::GaloisKeys &gal_keys, const seal::EncryptionParameters &params) {
+    auto context = seal::SEALContext::Create(params);
+    seal::Evaluator evaluator(context);
+    if (dimension < 1 || (int)V_diagonals.size() < dimension - 1 || (int)W_diagonals.size() < dimension - 1)
+        throw std::invalid_argument("dimension does not match the diagonal sets");
+    seal::Ciphertext A0 = Linear_Transform_Plain(ctA, U_sigma_diagonals, gal_keys, params);
+    seal::Ciphertext B0 = Linear_Transform_Plain(ctB, U_tau_diagonals, gal_keys, params);
+    seal::Ciphertext ctAB;
+    evaluator.multiply(A0, B0, ctAB);
+    evaluator.mod_switch_to_next_inplace(ctAB);
+    if (dimension == 1) return ctAB;
+    const int dd = (int)V_diagonals[0].size(), K1 = dimension - 1;
+    std::vector<int> steps(dd);
+    for (int l = 0; l < dd; l++) steps[l] = l;
+    auto shifted = [&](const seal::Ciphertext &base, const std::vector<std::vector<seal::Plaintext>> &sets) {
+        seal::Ciphertext dup = detail::duplicate(base, dd, gal_keys, evaluator);
+        const detail::Poly &pn = dup.poly();
+        detail::Batch rots = detail::rotate_all(pn.view(), pn.eng, pn.scale, gal_keys, steps);
+        double pscale = sets[0][0].poly().scale;
+        detail::scale_ok(*pn.eng, pn.scale * pscale, pn.limbs);
+        detail::Batch out(pn.eng, K1, 2, pn.limbs, pn.scale * pscale);
+        for (int k = 0; k < K1; k++) {
+            if ((int)sets[k].size() != dd) throw std::invalid_argument("encrypted and plain parameter mismatch");
+            detail::Batch diags = detail::gather(sets[k]);
+            if (diags.limbs != pn.limbs || diags.scale != pscale) throw std::invalid_argument("encrypted and plain parameter mismatch");
+            ckks_view vr = rots.view(), vd = diags.view(), vo = out.view();
+            vo.data += (std::size_t)k * out.entry_words();
+            vo.batch = 1;
+            detail::check(ckks_multiply_plain_sum(pn.eng->ctx, &vr, &vd, &vo, nullptr));
+        }
+        // rescale_to_next_inplace on every A_k / B_k, then the reference's "manual rescale" of the scale
+        detail::Batch low(pn.eng, K1, 2, pn.limbs - 1, 0.0);
+        if (pn.limbs < 2) throw std::invalid_argument("end of modulus switching chain reached");
+        ckks_view vi = out.view(), vl = low.view();
+        detail::check(ckks_rescale(pn.eng->ctx, &vi, &vl, nullptr));
+        low.scale = std::pow(2.0, (int)std::log2(out.scale / (double)pn.eng->primes[pn.limbs - 1]));
+        return low;
+    };
+    detail::Batch Ak = shifted(A0, V_diagonals), Bk = shifted(B0, W_diagonals);
+    detail::scale_ok(*Ak.e, Ak.scale * Bk.scale, Ak.limbs);
+    seal::Ciphertext rest;
+    rest.poly().allocate(Ak.e, 3, Ak.limbs);
+    rest.poly().scale = Ak.scale * Bk.scale;
+    ckks_view va = Ak.view(), vb = Bk.view(), vo = rest.poly().view();
+    detail::check(ckks_multiply_sum(Ak.e->ctx, &va, &vb, &vo, nullptr));
+    seal::Ciphertext out;
+    evaluator.add(ctAB, rest, out);
+    return out;
 }
 
 }  // namespace b200

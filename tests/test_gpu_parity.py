@@ -303,6 +303,8 @@ def test_large_batch_two_lanes_matches_oracle(make_fixture):
     (15, [60] + [40] * 19 + [60]),           # deepest chain SEAL allows at N = 32768 with 40-bit primes (880 of 881 bits)
     (15, [27] * 32),                         # most primes the engine accepts (K = 32), all on the FP64 path
     (13, [60, 60, 60]),                      # only large primes: everything on the integer path
+    (13, [50, 30, 30, 30, 30, 40]),          # large first prime, SMALL special prime: its limb comes from the FP64 kernel
+    (13, [40, 60, 40]),                      # a large prime between small ones, small special prime
 ])
 def test_extreme_modulus_chains(make_fixture, log_n, bits):
     """maximum / minimum sizes: relinearize, one Galois step and rescale stay bit-exact at the top level

@@ -122,3 +122,14 @@ def test_batched_helpers_bit_identical_to_reference_helpers(pkg, tmp_path):
     out = _run_ref("helper_driver", str(tmp_path))
     assert "ALL BIT-IDENTICAL" in out and "MISMATCH" not in out, out[-2000:]
     assert out.count("bit-identical") == 5
+
+
+@pytest.mark.gpu
+def test_batched_matrix_multiplication_bit_identical_to_reference(pkg, tmp_path):
+    """tests/cpp/matmul_driver.cpp: the reference's CC_Matrix_Multiplication (matrix_mult_benchmark.cpp,
+    compiled unchanged with main() renamed) against b200::CC_Matrix_Multiplication, d = 4: same words"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    out = _run_ref("matmul_driver", str(tmp_path))
+    assert "ALL BIT-IDENTICAL" in out and "MISMATCH" not in out, out[-2000:]
