@@ -320,3 +320,44 @@ def test_extreme_modulus_chains(make_fixture, log_n, bits):
         assert np.array_equal(fx.ev.apply_galois(d, g, fx.keys).numpy()[0], fx.orc.apply_galois(a2[0], g, fx.gks[g])), L
         if L > 1:
             assert np.array_equal(fx.ev.rescale_to_next(d).numpy()[0], fx.orc.rescale(a2[0])), L
+
+
+def _random_chains(count, seed=2024):
+    """prime-size patterns mixing both arithmetic paths (primes below 2^41 run on the FP64 pipe, larger
+    ones on the integer pipe; 41 and 42 bits straddle the boundary), total <= 218 bits (N = 8192)"""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        K = int(rng.integers(2, 7))
+        bits = [int(b) for b in rng.choice([28, 33, 36, 40, 41, 42, 47, 50, 60], size=K)]
+        if sum(bits) <= 218 and bits not in out:
+            out.append(bits)
+    return out
+
+
+@pytest.mark.parametrize("bits", _random_chains(10), ids=lambda b: "-".join(map(str, b)))
+def test_random_mixed_chains(make_fixture, bits):
+    """every placement of small / large primes (first, middle, special) keeps the key switch, the rotate-and-sum
+    chain and rescale bit-exact; batch 17 exercises the two-lane split"""
+    fx = make_fixture(13, bits, steps=(1,))
+    rng = np.random.default_rng(sum(bits))
+    g = fx.orc.galois_elt(1)
+    L = fx.L
+    a3 = fx.random_ct(rng, 1, 3, L)
+    assert np.array_equal(fx.ev.relinearize(fx.ctx.upload(a3), fx.keys).numpy()[0], fx.orc.relinearize(a3[0], fx.rlk))
+    a2 = fx.random_ct(rng, 17, 2, L)
+    d = fx.ctx.upload(a2)
+    got = fx.ev.apply_galois(d, g, fx.keys).numpy()
+    for b in (0, 8, 16):
+        assert np.array_equal(got[b], fx.orc.apply_galois(a2[b], g, fx.gks[g])), b
+    if L > 1:
+        assert np.array_equal(fx.ev.rescale_to_next(d).numpy()[3], fx.orc.rescale(a2[3]))
+    # two steps of the fused rotate-and-sum chain (graph replay) on the first entries
+    dup, acc = fx.ctx.upload(a2[:2]), fx.ctx.upload(a2[:2])
+    fx.ev.rotate_sum_chain(dup, acc, 1, 2, fx.keys)
+    want = a2[0]
+    r = a2[0]
+    for _ in range(2):
+        r = fx.orc.apply_galois(r, g, fx.gks[g])
+        want = fx.orc.add(want, r)
+    assert np.array_equal(acc.numpy()[0], want)
