@@ -582,6 +582,14 @@ def main():
     ap.add_argument("--no-fast", action="store_true", help="skip the informational doubling-mode epoch")
     ap.add_argument("--ncu", action="store_true", help="profiling run: one epoch between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # started as plain `python bench.py --gpus N`: relaunch as one process per GPU
+        import socket
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                                   "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -12,6 +12,7 @@
 //   Linear_Transform_Cipher           :212-234         b200::Linear_Transform_Cipher
 //   Linear_Transform_CipherMatrix_PlainVector :265-278 b200::Linear_Transform_CipherMatrix_PlainVector
 //   C_Matrix_Encode                   :307-322         b200::C_Matrix_Encode
+//   C_Matrix_Decode                   :325-360         b200::C_Matrix_Decode
 //   cipher_dot_product                :416-502         b200::cipher_dot_product
 //   CC_Matrix_Multiplication (matrix_mult_benchmark.cpp:13-71)  b200::CC_Matrix_Multiplication
 //
@@ -195,6 +196,40 @@ inline seal::Ciphertext C_Matrix_Encode(const std::vector<seal::Ciphertext> &mat
     out.poly().scale = rows.scale;
     ckks_view vr = rot.view(), vo = out.poly().view();
     detail::check(ckks_add_many(rows.e->ctx, &vr, &vo, nullptr));
+    return out;
+}
+
+// helper.h:325-360 -- split a packed matrix back into its d row ciphertexts: mask row i with ones (the d
+// masks are encoded as one batch on the device), then rotate_vector by i*d (one rotation plan)
+inline std::vector<seal::Ciphertext> C_Matrix_Decode(const seal::Ciphertext &matrix, int dimension, double scale,
+                                                     const seal::GaloisKeys &gal_keys, seal::CKKSEncoder &ckks_encoder,
+                                                     seal::Evaluator &) {
+    const detail::Poly &pm = matrix.poly();
+    if (!pm.buf) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    if (pm.size != 2) throw std::invalid_argument("encrypted size must be 2");
+    const int d = dimension, dd = d * d;
+    if (d < 1 || (std::size_t)dd > ckks_encoder.slot_count()) throw std::invalid_argument("values has invalid size");
+    if (pm.limbs != pm.eng->K - 1) throw std::invalid_argument("encrypted and plain parameter mismatch");   // masks are encoded at the top level
+    detail::scale_ok(*pm.eng, pm.scale * scale, pm.limbs);
+    std::vector<double> masks((std::size_t)d * dd, 0.0);
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) masks[(std::size_t)i * dd + j + i * d] = 1.0;
+    detail::DevBuf vals(pm.eng, masks.size());
+    detail::check(ckks_upload(pm.eng->ctx, vals.p, masks.data(), masks.size() * 8, nullptr));
+    detail::check(ckks_stream_sync(pm.eng->ctx, nullptr));   // `masks` is pageable host memory about to go out of scope
+    detail::Batch pts(pm.eng, d, 1, pm.limbs, scale);
+    ckks_view vp = pts.view();
+    detail::check(ckks_encode(pm.eng->ctx, reinterpret_cast<const double *>(vals.p), dd, scale, &vp, nullptr));
+    detail::Batch rows(pm.eng, d, 2, pm.limbs, pm.scale * scale);
+    ckks_view vm = pm.view(), vr = rows.view();
+    vm.batch = d;            // the same ciphertext for every mask
+    vm.batch_stride = 0;
+    detail::check(ckks_multiply_plain(pm.eng->ctx, &vm, &vp, &vr, nullptr));
+    std::vector<int> steps(d);
+    for (int i = 0; i < d; i++) steps[i] = i * d;
+    detail::Batch rot = detail::rotate_all(vr, pm.eng, rows.scale, gal_keys, steps);
+    std::vector<seal::Ciphertext> out(d);
+    for (int i = 0; i < d; i++) rot.get(i, out[i].poly());
     return out;
 }
 

@@ -123,6 +123,23 @@ int main() {
     t_got = timed(got, eng, [&] { return b200::C_Matrix_Encode(rows, gk, evaluator); });
     same("C_Matrix_Encode (12 rows)", ref, got, t_ref, t_got);
 
+    {   // C_Matrix_Decode of the packed matrix: d row ciphertexts, each compared
+        ckks_stream_sync(eng.ctx, nullptr);
+        auto t0 = chrono::high_resolution_clock::now();
+        vector<Ciphertext> r = C_Matrix_Decode(got, d, scale, gk, encoder, evaluator);
+        ckks_stream_sync(eng.ctx, nullptr);
+        auto t1 = chrono::high_resolution_clock::now();
+        vector<Ciphertext> g = b200::C_Matrix_Decode(got, d, scale, gk, encoder, evaluator);
+        ckks_stream_sync(eng.ctx, nullptr);
+        auto t2 = chrono::high_resolution_clock::now();
+        bool ok = r.size() == g.size();
+        for (size_t i = 0; ok && i < r.size(); i++) ok = r[i].scale() == g[i].scale() && words(r[i]) == words(g[i]);
+        cout << "C_Matrix_Decode (12 rows): " << (ok ? "bit-identical" : "MISMATCH") << "   reference sequence "
+             << chrono::duration<double, micro>(t1 - t0).count() << " us, batched " << chrono::duration<double, micro>(t2 - t1).count()
+             << " us" << endl;
+        if (!ok) failures++;
+    }
+
     const int size = 256;
     vector<double> a(size), b(size);
     double want = 0;

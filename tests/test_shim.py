@@ -104,7 +104,8 @@ def test_batched_helper_header_compiles(pkg, tmp_path):
     src.write_text('#include "ckks_b200_helper.h"\n'
                    "int main() { auto f = &b200::Linear_Transform_Plain; auto g = &b200::cipher_dot_product;\n"
                    "auto h = &b200::C_Matrix_Encode; auto i = &b200::Linear_Transform_Cipher;\n"
-                   "auto j = &b200::Linear_Transform_CipherMatrix_PlainVector; return (f && g && h && i && j) ? 0 : 1; }\n")
+                   "auto j = &b200::Linear_Transform_CipherMatrix_PlainVector; auto k = &b200::C_Matrix_Decode;\n"
+                   "auto l = &b200::CC_Matrix_Multiplication; return (f && g && h && i && j && k && l) ? 0 : 1; }\n")
     res = subprocess.run(["g++", "-std=c++17", "-Wall", "-O0"] + INC + [str(src), "-o", str(tmp_path / "use_helper"), LIB,
                           "-Wl,-rpath," + os.path.dirname(LIB)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout[-3000:]
@@ -121,7 +122,7 @@ def test_batched_helpers_bit_identical_to_reference_helpers(pkg, tmp_path):
         pytest.skip("no CUDA device")
     out = _run_ref("helper_driver", str(tmp_path))
     assert "ALL BIT-IDENTICAL" in out and "MISMATCH" not in out, out[-2000:]
-    assert out.count("bit-identical") == 5
+    assert out.count("bit-identical") == 6
 
 
 @pytest.mark.gpu
