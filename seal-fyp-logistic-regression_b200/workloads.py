@@ -314,11 +314,17 @@ class DiagonalSet:
     @staticmethod
     def from_matrix(U, eps, scale, encoder, limbs=None):
         n = U.shape[0]
-        diags = all_diagonals(U)
-        idx = [l for l in range(n) if np.any(diags[l] != 0.0)]
+        # only the non-empty diagonals are materialised: entry (r, c) lies on diagonal (c - r) mod n at
+        # position r  (diag_l[k] = U[k][(k+l) mod n], helper.h:175-209) -- O(nnz) instead of O(n^2)
+        r, c = np.nonzero(U)
+        l = (c - r) % n
+        idx = np.unique(l)
+        pos = np.searchsorted(idx, l)
+        vals = np.zeros((len(idx), n))
+        vals[pos, r] = U[r, c]
         default = encoder.encode(np.full(n, eps), scale, limbs=limbs)
-        special = encoder.encode(diags[idx] + eps, scale, limbs=limbs)
-        return DiagonalSet(n, default, idx, special)
+        special = encoder.encode(vals + eps, scale, limbs=limbs)
+        return DiagonalSet(n, default, [int(x) for x in idx], special)
 
 
 def linear_transform_plain_sparse(ev, ct, dset, keys, plans, rots=None, s_all=None):
