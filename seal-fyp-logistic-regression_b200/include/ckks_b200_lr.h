@@ -1,0 +1,216 @@
+// ckks_b200_lr.h -- the reference's encrypted logistic-regression functions on the batched engine (C++).
+//
+// Mirrors logistic_regression_ckks.cpp: Horner_cipher (:139-205), predict_cipher_weights (:208-266),
+// update_weights (:269-345) -- same names and argument order, in namespace b200 -- over cipher_dot_product
+// (helper.h:416-502).  The per-row / per-feature dot products, which the reference runs one evaluator call at
+// a time (R x (C+1) and C x (R+13) key switches), advance in lock-step as batched key switches and the fused
+// rotate-and-sum chain; every individual ciphertext still sees the reference's evaluator sequence.
+//
+// The committed program cannot finish an iteration (rows and weights packed at slot 0 while
+// the mask picks slot i; too few primes; scale / level mismatch before the final sub; "CIPHERTEXT IS
+// TRANSPARENT" at :336).  The repairs are those of lr.py, client-side only:
+//   R1  RowLayout: row i is encoded cyclically at slots i..i+C-1, the weights periodically, so the dot product of
+//       row i lands in slot i where the reference's one-hot mask e_i picks it up;
+//   R2  the chain needs 9 data primes ({60, 40 x 8, 60} at N = 32768);
+//   R3  after the learning-rate multiply the gradient is rescaled, and the weights are brought to its level
+//       and scale before sub;
+//   R6  the 1/8 input scaling of the sigmoid approximation is folded into the coefficients (sigmoid_coeffs).
+#pragma once
+#include "ckks_b200_helper.h"
+
+namespace b200 {
+
+// logistic_regression_ckks.cpp:247,251,255 divided by 8^i (R6); zero coefficients are 0.00001 there
+inline std::vector<double> sigmoid_coeffs(int degree) {
+    std::vector<double> c;
+    if (degree == 3) c = {0.5, 1.20069, 0.00001, -0.81562};
+    else if (degree == 5) c = {0.5, 1.53048, 0.00001, -2.3533056, 0.00001, 1.3511295};
+    else if (degree == 7) c = {0.5, 1.73496, 0.00001, -4.19407, 0.00001, 5.43402, 0.00001, -2.50739};
+    else throw std::invalid_argument("Invalid DEGREE");
+    double p = 1.0;
+    for (auto &x : c) x /= p, p *= 8.0;
+    return c;
+}
+
+// client-side packing for R samples x C features in N/2 slots (R1): needs R + C <= slots and 2R <= slots
+struct RowLayout {
+    int R, C;
+    std::size_t slots;
+    RowLayout(int rows, int cols, std::size_t slot_count) : R(rows), C(cols), slots(slot_count) {
+        if ((std::size_t)(R + C) > slots || (std::size_t)(2 * R) > slots) throw std::invalid_argument("R + C and 2R must fit in N/2 slots");
+    }
+    std::vector<double> row(const std::vector<std::vector<double>> &X, int i) const {
+        std::vector<double> v(slots, 0.0);
+        for (int s = i; s < i + C; s++) v[s] = X[i][s % C];
+        return v;
+    }
+    std::vector<double> column(const std::vector<std::vector<double>> &X, int j) const {
+        std::vector<double> v(slots, 0.0);
+        for (int i = 0; i < R; i++) v[i] = X[i][j];
+        return v;
+    }
+    std::vector<double> weights(const std::vector<double> &w) const {
+        std::vector<double> v(slots, 0.0);
+        for (int s = 0; s < R + C; s++) v[s] = w[s % C];
+        return v;
+    }
+    std::vector<double> labels(const std::vector<double> &y) const {
+        std::vector<double> v(slots, 0.0);
+        for (int i = 0; i < R; i++) v[i] = y[i];
+        return v;
+    }
+};
+
+// logistic_regression_ckks.cpp:139-205 -- (((a_D) x + a_{D-1}) x + ...) with the reference's level alignment and
+// "manual rescale"; one ciphertext, sequential, through the shim's evaluator
+inline seal::Ciphertext Horner_cipher(seal::Ciphertext ctx, int degree, const std::vector<double> &coeffs,
+                                      seal::CKKSEncoder &ckks_encoder, double scale, seal::Evaluator &evaluator,
+                                      seal::Encryptor &encryptor, const seal::RelinKeys &relin_keys, const seal::EncryptionParameters &) {
+    if ((int)coeffs.size() != degree + 1) throw std::invalid_argument("coeffs has invalid size");
+    std::vector<seal::Plaintext> plain_coeffs(degree + 1);
+    for (int i = 0; i <= degree; i++) ckks_encoder.encode(coeffs[i], scale, plain_coeffs[i]);
+    seal::Ciphertext temp;
+    encryptor.encrypt(plain_coeffs[degree], temp);
+    for (int i = degree - 1; i >= 0; i--) {
+        if (ctx.coeff_mod_count() > temp.coeff_mod_count()) evaluator.mod_switch_to_inplace(ctx, temp.parms_id());
+        else if (ctx.coeff_mod_count() < temp.coeff_mod_count()) evaluator.mod_switch_to_inplace(temp, ctx.parms_id());
+        evaluator.multiply_inplace(temp, ctx);
+        evaluator.relinearize_inplace(temp, relin_keys);
+        evaluator.rescale_to_next_inplace(temp);
+        evaluator.mod_switch_to_inplace(plain_coeffs[i], temp.parms_id());
+        temp.scale() = std::pow(2.0, 40);
+        evaluator.add_plain_inplace(temp, plain_coeffs[i]);
+    }
+    return temp;
+}
+
+namespace detail {
+
+// first `limbs` limbs of every object (mod_switch_to_inplace of each, then gather)
+template <class T>
+inline Batch gather_at(const std::vector<T> &objs, int limbs) {
+    if (objs.empty()) throw std::invalid_argument("encrypteds cannot be empty");
+    const Poly &p0 = objs[0].poly();
+    if (!p0.buf || limbs < 1 || limbs > p0.limbs) throw std::invalid_argument("cannot switch to higher level modulus");
+    Batch b(p0.eng, (int)objs.size(), p0.size, limbs, p0.scale);
+    const std::size_t n = p0.eng->n;
+    for (std::size_t i = 0; i < objs.size(); i++) {
+        const Poly &p = objs[i].poly();
+        if (!p.buf || p.size != p0.size || p.limbs != p0.limbs) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+        if (p.scale != p0.scale) throw std::invalid_argument("scale mismatch");
+        for (int k = 0; k < p.size; k++)
+            check(ckks_copy(p0.eng->ctx, b.buf->p + i * b.entry_words() + (std::size_t)k * limbs * n, p.buf->p + (std::size_t)k * p.cap * n,
+                            (std::size_t)limbs * n * 8, nullptr));
+    }
+    return b;
+}
+
+// cipher_dot_product (helper.h:416-502) of every entry of `a` with `b` (one ciphertext for all entries), in lock-step
+inline Batch dot_product_batch(const Batch &a, const Poly &b, int size, const seal::RelinKeys &rk, const seal::GaloisKeys &gk) {
+    if (a.size != 2 || b.size != 2) throw std::invalid_argument("encrypted size must be 2");
+    if (a.limbs != b.limbs) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+    if (a.limbs < 2) throw std::invalid_argument("end of modulus switching chain reached");
+    if (!rk.s || !rk.s->keys.count(0)) throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+    if (!gk.s || !gk.s->ks) throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+    const auto &e = a.e;
+    const int B = a.batch, L = a.limbs;
+    scale_ok(*e, a.scale * b.scale, L);
+    Batch prod(e, B, 3, L, a.scale * b.scale), lin(e, B, 2, L, prod.scale);
+    ckks_view va = a.view(), vb = b.view(), vp = prod.view(), vl = lin.view();
+    vb.limbs = L;
+    check(ckks_multiply(e->ctx, &va, &vb, &vp, nullptr));
+    check(ckks_relinearize(e->ctx, &vp, rk.s->keys.at(0)->p, &vl, nullptr));
+    Batch mult(e, B, 2, L - 1, prod.scale / (double)e->primes[L - 1]);
+    ckks_view vm = mult.view();
+    check(ckks_rescale(e->ctx, &vl, &vm, nullptr));
+    Batch rot(e, B, 2, L - 1, mult.scale), scratch(e, B, 2, L - 1, mult.scale), dup(e, B, 2, L - 1, mult.scale);
+    ckks_view vr = rot.view(), vs = scratch.view(), vd = dup.view();
+    check(ckks_rotate(e->ctx, gk.s->ks, &vm, -size, &vr, &vs, nullptr));          // "vector has zeros now"
+    check(ckks_add(e->ctx, &vm, &vr, &vd, nullptr));                               // "vector has duplicate now"
+    if (size > 1) {
+        int final_in_b = 0;
+        check(ckks_rotate_sum_chain(e->ctx, gk.s->ks, &vd, &vs, &vm, 1, size - 1, &final_in_b, nullptr));
+    }
+    mult.scale = std::pow(2.0, (int)std::log2(mult.scale));
+    return mult;
+}
+
+// one-hot masks e_0..e_{count-1} (length `length`), encoded as one batch at `limbs`
+inline Batch one_hot_masks(const std::shared_ptr<Engine> &e, int count, int length, double scale, int limbs) {
+    std::vector<double> m((std::size_t)count * length, 0.0);
+    for (int i = 0; i < count; i++) m[(std::size_t)i * length + i] = 1.0;
+    DevBuf vals(e, m.size());
+    check(ckks_upload(e->ctx, vals.p, m.data(), m.size() * 8, nullptr));
+    check(ckks_stream_sync(e->ctx, nullptr));
+    Batch pts(e, count, 1, limbs, scale);
+    ckks_view vp = pts.view();
+    check(ckks_encode(e->ctx, reinterpret_cast<const double *>(vals.p), length, scale, &vp, nullptr));
+    return pts;
+}
+
+// multiply_plain_inplace of every entry with its mask, add_many, rescale, "manual rescale" of the scale
+inline seal::Ciphertext masked_sum(const Batch &cts, const Batch &masks, seal::Evaluator &evaluator) {
+    scale_ok(*cts.e, cts.scale * masks.scale, cts.limbs);
+    seal::Ciphertext sum;
+    sum.poly().allocate(cts.e, 2, cts.limbs);
+    sum.poly().scale = cts.scale * masks.scale;
+    ckks_view vc = cts.view(), vm = masks.view(), vo = sum.poly().view();
+    check(ckks_multiply_plain_sum(cts.e->ctx, &vc, &vm, &vo, nullptr));
+    evaluator.rescale_to_next_inplace(sum);          // relinearize_inplace on a size-2 ciphertext is a no-op (:236, :318)
+    sum.scale() = std::pow(2.0, (int)std::log2(sum.scale()));
+    return sum;
+}
+
+}  // namespace detail
+
+// logistic_regression_ckks.cpp:208-266 -- sigmoid polynomial of the R per-row dot products, slot i = row i
+inline seal::Ciphertext predict_cipher_weights(const std::vector<seal::Ciphertext> &features, const seal::Ciphertext &weights,
+                                               int num_weights, double scale, seal::Evaluator &evaluator,
+                                               seal::CKKSEncoder &ckks_encoder, const seal::GaloisKeys &gal_keys,
+                                               const seal::RelinKeys &relin_keys, seal::Encryptor &encryptor,
+                                               const seal::EncryptionParameters &params, int degree = 3) {
+    const int num_rows = (int)features.size();
+    detail::Batch rows = detail::gather(features);
+    if (!weights.poly().buf) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    detail::Batch results = detail::dot_product_batch(rows, weights.poly(), num_weights, relin_keys, gal_keys);
+    // masks are encoded at the top level and mod-switched to the next one (:225-227) = encoded at that level
+    detail::Batch masks = detail::one_hot_masks(rows.e, num_rows, num_rows, scale, rows.limbs - 1);
+    seal::Ciphertext lintransf_vec = detail::masked_sum(results, masks, evaluator);
+    std::vector<double> coeffs = sigmoid_coeffs(degree);
+    return Horner_cipher(lintransf_vec, degree, coeffs, ckks_encoder, scale, evaluator, encryptor, relin_keys, params);
+}
+
+// logistic_regression_ckks.cpp:269-345 -- weights - learning_rate / R * X^T (sigmoid(X w) - y), with repair R3
+inline seal::Ciphertext update_weights(const std::vector<seal::Ciphertext> &features, const std::vector<seal::Ciphertext> &features_T,
+                                       seal::Ciphertext labels, const seal::Ciphertext &weights, float learning_rate,
+                                       seal::Evaluator &evaluator, seal::CKKSEncoder &ckks_encoder, const seal::GaloisKeys &gal_keys,
+                                       const seal::RelinKeys &relin_keys, seal::Encryptor &encryptor, double scale,
+                                       const seal::EncryptionParameters &params, int degree = 3) {
+    const int num_observations = (int)features.size(), num_weights = (int)features_T.size();
+    seal::Ciphertext predictions = predict_cipher_weights(features, weights, num_weights, scale, evaluator, ckks_encoder, gal_keys,
+                                                          relin_keys, encryptor, params, degree);
+    evaluator.mod_switch_to_inplace(labels, predictions.parms_id());
+    predictions.scale() = labels.scale();             // both are 2^40 after the forced scales
+    seal::Ciphertext pred_labels;
+    evaluator.sub(predictions, labels, pred_labels);
+    const int Lg = (int)pred_labels.coeff_mod_count();
+    detail::Batch cols = detail::gather_at(features_T, Lg);                                      // :295
+    detail::Batch grads = detail::dot_product_batch(cols, pred_labels.poly(), num_observations, relin_keys, gal_keys);
+    detail::Batch masks = detail::one_hot_masks(cols.e, num_weights, num_weights, scale, grads.limbs);   // :305-308
+    seal::Ciphertext gradient = detail::masked_sum(grads, masks, evaluator);
+    seal::Plaintext N_pt;
+    ckks_encoder.encode((double)learning_rate / num_observations, scale, N_pt);                  // :330-333
+    evaluator.mod_switch_to_inplace(N_pt, gradient.parms_id());
+    evaluator.multiply_plain_inplace(gradient, N_pt);
+    evaluator.rescale_to_next_inplace(gradient);                                                 // R3
+    gradient.scale() = std::pow(2.0, (int)std::log2(gradient.scale()));
+    seal::Ciphertext w_low = weights;
+    evaluator.mod_switch_to_inplace(w_low, gradient.parms_id());                                 // R3
+    w_low.scale() = gradient.scale();
+    seal::Ciphertext new_weights;
+    evaluator.sub(gradient, w_low, new_weights);                                                 // :341
+    evaluator.negate_inplace(new_weights);                                                       // :342
+    return new_weights;
+}
+
+}  // namespace b200

@@ -21,3 +21,6 @@ echo "built helper_driver"
 g++ -std=c++17 -O2 -w -I "$ROOT/include" -I "$PKG/include" -I "$REF" "$ROOT/tests/cpp/matmul_driver.cpp" -o "$OUT/matmul_driver" \
     "$PKG/libckks_b200.so" -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../../../seal-fyp-logistic-regression_b200'
 echo "built matmul_driver"
+g++ -std=c++17 -O2 -Wall -I "$ROOT/include" -I "$PKG/include" "$ROOT/tests/cpp/lr_driver.cpp" -o "$OUT/lr_driver" \
+    "$PKG/libckks_b200.so" -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../../../seal-fyp-logistic-regression_b200'
+echo "built lr_driver"

@@ -134,3 +134,30 @@ def test_batched_matrix_multiplication_bit_identical_to_reference(pkg, tmp_path)
         pytest.skip("no CUDA device")
     out = _run_ref("matmul_driver", str(tmp_path))
     assert "ALL BIT-IDENTICAL" in out and "MISMATCH" not in out, out[-2000:]
+
+
+def test_batched_lr_header_compiles(pkg, tmp_path):
+    """ckks_b200_lr.h (b200::Horner_cipher / predict_cipher_weights / update_weights) compiles and links
+    without the reference tree"""
+    exe = str(tmp_path / "lr_driver")
+    res = subprocess.run(["g++", "-std=c++17", "-Wall", "-O0"] + INC + [os.path.join(ROOT, "tests", "cpp", "lr_driver.cpp"), "-o", exe, LIB,
+                          "-Wl,-rpath," + os.path.dirname(LIB)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout[-3000:]
+
+
+@pytest.mark.gpu
+def test_cpp_lr_iteration_matches_plaintext(pkg, tmp_path):
+    """tests/cpp/lr_driver.cpp: one encrypted training iteration through the C++ batched LR functions
+    (b200::update_weights, 64 rows x 4 features, N = 32768, degree-3 Horner sigmoid): decrypted predictions and
+    updated weights equal the plaintext computation within 1e-3"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    exe = os.path.join(REF_BUILD, "lr_driver")
+    if not os.path.exists(exe):
+        exe = str(tmp_path / "lr_driver")
+        res = subprocess.run(["g++", "-std=c++17", "-O2"] + INC + [os.path.join(ROOT, "tests", "cpp", "lr_driver.cpp"), "-o", exe, LIB,
+                              "-Wl,-rpath," + os.path.dirname(LIB)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert res.returncode == 0, res.stdout[-3000:]
+    res = subprocess.run([exe, "64"], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "LR OK" in res.stdout, res.stdout[-2000:]
