@@ -1,6 +1,6 @@
 // ckks_b200_lr.h -- the reference's encrypted logistic-regression functions on the batched engine (C++).
 //
-// Mirrors logistic_regression_ckks.cpp: Horner_cipher (:139-205), predict_cipher_weights (:208-266),
+// Mirrors logistic_regression_ckks.cpp: Tree_cipher (:55-137), Horner_cipher (:139-205), predict_cipher_weights (:208-266),
 // update_weights (:269-345) -- same names and argument order, in namespace b200 -- over cipher_dot_product
 // (helper.h:416-502).  The per-row / per-feature dot products, which the reference runs one evaluator call at
 // a time (R x (C+1) and C x (R+13) key switches), advance in lock-step as batched key switches and the fused
@@ -16,6 +16,8 @@
 //       and scale before sub;
 //   R6  the 1/8 input scaling of the sigmoid approximation is folded into the coefficients (sigmoid_coeffs).
 #pragma once
+#include <algorithm>
+
 #include "ckks_b200_helper.h"
 
 namespace b200 {
@@ -82,6 +84,51 @@ inline seal::Ciphertext Horner_cipher(seal::Ciphertext ctx, int degree, const st
         evaluator.add_plain_inplace(temp, plain_coeffs[i]);
     }
     return temp;
+}
+
+// helper.h:505-547 -- x^2..x^degree, each power from the split that minimises multiplicative depth
+inline void compute_all_powers(const seal::Ciphertext &ctx, int degree, seal::Evaluator &evaluator, const seal::RelinKeys &relin_keys,
+                               std::vector<seal::Ciphertext> &powers) {
+    powers.assign(degree + 1, seal::Ciphertext());
+    powers[1] = ctx;
+    std::vector<int> levels(degree + 1, 0);
+    for (int i = 2; i <= degree; i++) {
+        int minlevel = i, cand = -1;
+        for (int j = 1; j <= i / 2; j++) {
+            const int newlevel = std::max(levels[j], levels[i - j]) + 1;
+            if (newlevel < minlevel) cand = j, minlevel = newlevel;
+        }
+        levels[i] = minlevel;
+        if (cand < 0) throw std::runtime_error("error");
+        seal::Ciphertext temp = powers[cand];
+        evaluator.mod_switch_to_inplace(temp, powers[i - cand].parms_id());
+        evaluator.multiply(temp, powers[i - cand], powers[i]);
+        evaluator.relinearize_inplace(powers[i], relin_keys);
+        evaluator.rescale_to_next_inplace(powers[i]);
+    }
+}
+
+// logistic_regression_ckks.cpp:55-137 -- a_0 + sum_i a_i x^i from the power tree (depth ceil(log2 degree) + 1)
+inline seal::Ciphertext Tree_cipher(const seal::Ciphertext &ctx, int degree, double scale, const std::vector<double> &coeffs,
+                                    seal::CKKSEncoder &ckks_encoder, seal::Evaluator &evaluator, seal::Encryptor &encryptor,
+                                    const seal::RelinKeys &relin_keys, const seal::EncryptionParameters &) {
+    if ((int)coeffs.size() != degree + 1) throw std::invalid_argument("coeffs has invalid size");
+    std::vector<seal::Plaintext> plain_coeffs(degree + 1);
+    for (int i = 0; i <= degree; i++) ckks_encoder.encode(coeffs[i], scale, plain_coeffs[i]);
+    std::vector<seal::Ciphertext> powers;
+    compute_all_powers(ctx, degree, evaluator, relin_keys, powers);
+    seal::Ciphertext enc_result, temp;
+    encryptor.encrypt(plain_coeffs[0], enc_result);
+    for (int i = 1; i <= degree; i++) {
+        evaluator.mod_switch_to_inplace(plain_coeffs[i], powers[i].parms_id());
+        evaluator.multiply_plain(powers[i], plain_coeffs[i], temp);
+        evaluator.rescale_to_next_inplace(temp);
+        evaluator.mod_switch_to_inplace(enc_result, temp.parms_id());
+        enc_result.scale() = std::pow(2.0, (int)std::log2(enc_result.scale()));
+        temp.scale() = std::pow(2.0, (int)std::log2(enc_result.scale()));
+        evaluator.add_inplace(enc_result, temp);
+    }
+    return enc_result;
 }
 
 namespace detail {
@@ -168,7 +215,7 @@ inline seal::Ciphertext predict_cipher_weights(const std::vector<seal::Ciphertex
                                                int num_weights, double scale, seal::Evaluator &evaluator,
                                                seal::CKKSEncoder &ckks_encoder, const seal::GaloisKeys &gal_keys,
                                                const seal::RelinKeys &relin_keys, seal::Encryptor &encryptor,
-                                               const seal::EncryptionParameters &params, int degree = 3) {
+                                               const seal::EncryptionParameters &params, int degree = 3, bool tree = false) {
     const int num_rows = (int)features.size();
     detail::Batch rows = detail::gather(features);
     if (!weights.poly().buf) throw std::invalid_argument("encrypted is not valid for encryption parameters");
@@ -177,6 +224,7 @@ inline seal::Ciphertext predict_cipher_weights(const std::vector<seal::Ciphertex
     detail::Batch masks = detail::one_hot_masks(rows.e, num_rows, num_rows, scale, rows.limbs - 1);
     seal::Ciphertext lintransf_vec = detail::masked_sum(results, masks, evaluator);
     std::vector<double> coeffs = sigmoid_coeffs(degree);
+    if (tree) return Tree_cipher(lintransf_vec, degree, scale, coeffs, ckks_encoder, evaluator, encryptor, relin_keys, params);
     return Horner_cipher(lintransf_vec, degree, coeffs, ckks_encoder, scale, evaluator, encryptor, relin_keys, params);
 }
 
@@ -185,10 +233,10 @@ inline seal::Ciphertext update_weights(const std::vector<seal::Ciphertext> &feat
                                        seal::Ciphertext labels, const seal::Ciphertext &weights, float learning_rate,
                                        seal::Evaluator &evaluator, seal::CKKSEncoder &ckks_encoder, const seal::GaloisKeys &gal_keys,
                                        const seal::RelinKeys &relin_keys, seal::Encryptor &encryptor, double scale,
-                                       const seal::EncryptionParameters &params, int degree = 3) {
+                                       const seal::EncryptionParameters &params, int degree = 3, bool tree = false) {
     const int num_observations = (int)features.size(), num_weights = (int)features_T.size();
     seal::Ciphertext predictions = predict_cipher_weights(features, weights, num_weights, scale, evaluator, ckks_encoder, gal_keys,
-                                                          relin_keys, encryptor, params, degree);
+                                                          relin_keys, encryptor, params, degree, tree);
     evaluator.mod_switch_to_inplace(labels, predictions.parms_id());
     predictions.scale() = labels.scale();             // both are 2^40 after the forced scales
     seal::Ciphertext pred_labels;

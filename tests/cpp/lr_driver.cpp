@@ -81,6 +81,21 @@ int main(int argc, char **argv) {
     cout << "predict_cipher_weights: max |decrypt - sigmoid_poly(X w)| = " << err << " over " << R << " rows" << endl;
     if (!(err < 1e-3)) failures++;
 
+    {   // the tree method, degree 7 (the sigmoid of config 5): same rows, deeper polynomial
+        vector<double> c7 = b200::sigmoid_coeffs(7);
+        Ciphertext p7 = b200::predict_cipher_weights(rows, weights, C, scale, evaluator, encoder, gk, rk, encryptor, params, 7, true);
+        vector<double> g7 = dec(p7);
+        double e7 = 0;
+        for (int i = 0; i < R; i++) {
+            double z = 0, s = 0, pw = 1;
+            for (int j = 0; j < C; j++) z += X[i][j] * w[j];
+            for (double c : c7) s += c * pw, pw *= z;
+            e7 = max(e7, fabs(g7[i] - s));
+        }
+        cout << "predict_cipher_weights (Tree_cipher, degree 7): max error " << e7 << endl;
+        if (!(e7 < 1e-3)) failures++;
+    }
+
     auto &eng = *weights.poly().eng;
     ckks_stream_sync(eng.ctx, nullptr);
     auto t0 = chrono::high_resolution_clock::now();
