@@ -1,7 +1,7 @@
 // ckks_b200_lr.h -- the reference's encrypted logistic-regression functions on the batched engine (C++).
 //
 // Mirrors logistic_regression_ckks.cpp: Tree_cipher (:55-137), Horner_cipher (:139-205), predict_cipher_weights (:208-266),
-// update_weights (:269-345) -- same names and argument order, in namespace b200 -- over cipher_dot_product
+// update_weights (:269-345), train_cipher (:348-385) -- same names and argument order, in namespace b200 -- over cipher_dot_product
 // (helper.h:416-502).  The per-row / per-feature dot products, which the reference runs one evaluator call at
 // a time (R x (C+1) and C x (R+13) key switches), advance in lock-step as batched key switches and the fused
 // rotate-and-sum chain; every individual ciphertext still sees the reference's evaluator sequence.
@@ -14,6 +14,7 @@
 //   R2  the chain needs 9 data primes ({60, 40 x 8, 60} at N = 32768);
 //   R3  after the learning-rate multiply the gradient is rescaled, and the weights are brought to its level
 //       and scale before sub;
+//   R4  train_cipher re-encodes the decoded weights at the top level instead of re-encrypting the exhausted plaintext;
 //   R6  the 1/8 input scaling of the sigmoid approximation is folded into the coefficients (sigmoid_coeffs).
 #pragma once
 #include <algorithm>
@@ -258,6 +259,33 @@ inline seal::Ciphertext update_weights(const std::vector<seal::Ciphertext> &feat
     seal::Ciphertext new_weights;
     evaluator.sub(gradient, w_low, new_weights);                                                 // :341
     evaluator.negate_inplace(new_weights);                                                       // :342
+    return new_weights;
+}
+
+// logistic_regression_ckks.cpp:348-385 -- `iters` training iterations; the weights are refreshed after each one
+// by the party holding the secret key (decrypt, decode, re-encode, encrypt).  Repair R4: the reference
+// re-encrypts the low-level plaintext it just decrypted, which leaves no levels for the next iteration; here
+// the decoded weights are re-packed periodically (RowLayout::weights) and encoded at the top level.
+inline seal::Ciphertext train_cipher(const std::vector<seal::Ciphertext> &features, const std::vector<seal::Ciphertext> &features_T,
+                                     const seal::Ciphertext &labels, const seal::Ciphertext &weights, float learning_rate, int iters,
+                                     int observations, int num_weights, seal::Evaluator &evaluator, seal::CKKSEncoder &ckks_encoder,
+                                     double scale, const seal::GaloisKeys &gal_keys, const seal::RelinKeys &relin_keys,
+                                     seal::Encryptor &encryptor, seal::Decryptor &decryptor, const seal::EncryptionParameters &params,
+                                     int degree = 3, bool tree = false) {
+    RowLayout layout(observations, num_weights, ckks_encoder.slot_count());
+    seal::Ciphertext new_weights = weights;
+    for (int i = 0; i < iters; i++) {
+        new_weights = update_weights(features, features_T, labels, new_weights, learning_rate, evaluator, ckks_encoder, gal_keys,
+                                     relin_keys, encryptor, scale, params, degree, tree);
+        seal::Plaintext new_weights_pt;
+        decryptor.decrypt(new_weights, new_weights_pt);
+        std::vector<double> decoded;
+        ckks_encoder.decode(new_weights_pt, decoded);
+        decoded.resize(num_weights);
+        seal::Plaintext fresh;
+        ckks_encoder.encode(layout.weights(decoded), scale, fresh);
+        encryptor.encrypt(fresh, new_weights);
+    }
     return new_weights;
 }
 
