@@ -161,3 +161,39 @@ def test_cpp_lr_iteration_matches_plaintext(pkg, tmp_path):
         assert res.returncode == 0, res.stdout[-3000:]
     res = subprocess.run([exe, "64"], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0 and "LR OK" in res.stdout, res.stdout[-2000:]
+
+
+def _build_host_checks(tmp_path):
+    exe = str(tmp_path / "host_checks")
+    res = subprocess.run(["g++", "-std=c++17", "-Wall", "-O0"] + INC + [os.path.join(ROOT, "tests", "cpp", "host_checks.cpp"), "-o", exe, LIB,
+                          "-Wl,-rpath," + os.path.dirname(LIB)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout[-3000:]
+    return exe
+
+
+def test_cpp_row_layout_matches_python(pkg, tmp_path):
+    """b200::RowLayout / sigmoid_coeffs (ckks_b200_lr.h) pack exactly like lr.RowLayout / folded_coeffs"""
+    import importlib
+    import numpy as np
+    lr = importlib.import_module("seal-fyp-logistic-regression_b200.lr")
+    out = subprocess.run([_build_host_checks(tmp_path), "layout"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    rows = [np.array([float(x) for x in line.split()]) for line in out.strip().splitlines()]
+    R, C = 5, 3
+    X = np.array([[10 * i + j + 1 for j in range(C)] for i in range(R)], dtype=float)
+    lay = lr.RowLayout(R, C, 16)
+    assert np.array_equal(np.stack(rows[:R]), lay.rows(X))
+    assert np.array_equal(np.stack(rows[R:R + C]), lay.columns(X))
+    assert np.array_equal(rows[R + C], lay.weights(np.array([0.5, -1.5, 2.5])))
+    assert np.array_equal(rows[R + C + 1], lay.labels(np.array([1, 0, 1, 1, 0.0])))
+    for k, d in enumerate((3, 5, 7)):
+        assert np.allclose(rows[R + C + 2 + k], lr.folded_coeffs(d), rtol=1e-15, atol=0)
+
+
+def test_shim_fails_loudly_without_gpu(pkg, tmp_path):
+    """no CPU fallback: on a machine without a CUDA device the first SEALContext::Create throws with the
+    engine's message instead of computing anything on the host"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    res = subprocess.run([_build_host_checks(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 3 and "no CUDA device" in res.stdout, res.stdout
