@@ -149,6 +149,21 @@ def update_weights(ev, features, features_T, labels, weights, lr, scale, keys, e
     return ev.negate_inplace(new_weights)                                 # :342
 
 
+def train_cipher(ev, features, features_T, labels, weights, lr, iters, layout, scale, keys, encoder, encryptor, decryptor,
+                 degree=3, method="horner"):
+    """train_cipher (logistic_regression_ckks.cpp:348-385): `iters` x (update_weights, then the key holder
+    decrypts, decodes and re-encrypts the weights).  Repair R4: the decoded weights are re-packed
+    (RowLayout.weights) and encoded at the top level -- the reference re-encrypts the exhausted low-level
+    plaintext, which leaves the next iteration without levels (:376-381)."""
+    new_weights = weights
+    for _ in range(iters):
+        new_weights = update_weights(ev, features, features_T, labels, new_weights, lr, scale, keys, encoder, encryptor,
+                                     degree=degree, method=method)
+        decoded = encoder.decode(decryptor.decrypt(new_weights))[0, : layout.C]
+        new_weights = encryptor.encrypt(encoder.encode(layout.weights(decoded), scale))
+    return new_weights
+
+
 class ColumnLayout:
     """config 5 packing: mini-batch m holds samples [m*B, (m+1)*B) as C column ciphertexts"""
 

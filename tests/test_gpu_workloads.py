@@ -269,6 +269,38 @@ def test_client_objects_tolerance(make_fixture):
     assert cl.limbs == 1 and np.abs(enc.decode(decr.decrypt(cl))[:, :200] - x).max() < 2.0 ** -10
 
 
+def test_train_cipher_two_iterations(eng):
+    """train_cipher (logistic_regression_ckks.cpp:348-385, repair R4): two iterations with the weights
+    refreshed by the key holder in between, against two steps of plaintext LR (product-side keys and
+    encoder; one iteration with a degree-3 Horner sigmoid uses all 9 levels of {60, 40 x 8, 60})"""
+    wl, lr, client = _mods()
+    params = importlib.import_module(PKG + ".params")
+    ctx = eng.Context(15, params.coeff_modulus_create(15, [60] + [40] * 8 + [60]))
+    ev = eng.Evaluator(ctx)
+    enc = client.CKKSEncoder(ctx)
+    kg = client.KeyGenerator(ctx, seed=21)
+    keys = kg.keyset(steps=[1, -4, -8])
+    encr = client.Encryptor(ctx, kg.public_key(), seed=22)
+    decr = client.Decryptor(ctx, kg.secret_key())
+    rng = np.random.default_rng(23)
+    scale, R, C, degree = 2.0 ** 40, 8, 4, 3
+    X = rng.normal(0, 1, (R, C))
+    y = (rng.uniform(0, 1, R) > 0.5).astype(float)
+    w0 = rng.uniform(-2, 2, C)
+    lay = lr.RowLayout(R, C, ctx.n // 2)
+    rows = encr.encrypt(enc.encode(lay.rows(X), scale))
+    cols = encr.encrypt(enc.encode(lay.columns(X), scale))
+    labs = encr.encrypt(enc.encode(lay.labels(y), scale))
+    wct = encr.encrypt(enc.encode(lay.weights(w0), scale))
+    out = lr.train_cipher(ev, rows, cols, labs, wct, 0.1, 2, lay, scale, keys, enc, encr, decr, degree=degree)
+    assert out.limbs == ctx.top_limbs                       # refreshed: back at the top level
+    want = w0
+    for _ in range(2):
+        want = lr.plain_epoch(X, y, want, 0.1, degree)
+    got = enc.decode(decr.decrypt(out))[0, :C]
+    assert np.abs(got - want).max() < 1e-3
+
+
 def test_column_layout_epoch_matches_plaintext(make_fixture):
     """config-5 layout at a reduced size (C = 4 features, 2 mini-batches of B = 16 samples,
     tree degree 7): decrypted gradient and updated weights vs plaintext LR"""
