@@ -191,7 +191,7 @@ __global__ void k_dec_gather(const double2 *v, const uint32_t *kidx, double *val
 // (sigma 3.2, clipped at 6 sigma) and sample_poly_uniform.  Philox4x32-10 keyed by the caller's seed,
 // counter = (coefficient, polynomial, stream id): reproducible and order-independent.  Philox is a
 // statistical generator, not a CSPRNG -- the same holds for the std::mt19937_64 it replaces; a
-// deployment swaps in AES-CTR here (DESIGN.md section 8).
+// deployment swaps in AES-CTR here (DESIGN.md section 9).
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
