@@ -154,18 +154,18 @@ inline Batch gather_at(const std::vector<T> &objs, int limbs) {
 }
 
 // cipher_dot_product (helper.h:416-502) of every entry of `a` with `b` (one ciphertext for all entries), in lock-step
-inline Batch dot_product_batch(const Batch &a, const Poly &b, int size, const seal::RelinKeys &rk, const seal::GaloisKeys &gk) {
-    if (a.size != 2 || b.size != 2) throw std::invalid_argument("encrypted size must be 2");
-    if (a.limbs != b.limbs) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+inline Batch dot_product_batch(const Batch &a, ckks_view vb, double b_scale, int size, const seal::RelinKeys &rk,
+                               const seal::GaloisKeys &gk) {
+    if (a.size != 2 || vb.size != 2) throw std::invalid_argument("encrypted size must be 2");
+    if (a.limbs != vb.limbs || (vb.batch != 1 && vb.batch != a.batch)) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
     if (a.limbs < 2) throw std::invalid_argument("end of modulus switching chain reached");
     if (!rk.s || !rk.s->keys.count(0)) throw std::invalid_argument("relin_keys is not valid for encryption parameters");
     if (!gk.s || !gk.s->ks) throw std::invalid_argument("galois_keys is not valid for encryption parameters");
     const auto &e = a.e;
     const int B = a.batch, L = a.limbs;
-    scale_ok(*e, a.scale * b.scale, L);
-    Batch prod(e, B, 3, L, a.scale * b.scale), lin(e, B, 2, L, prod.scale);
-    ckks_view va = a.view(), vb = b.view(), vp = prod.view(), vl = lin.view();
-    vb.limbs = L;
+    scale_ok(*e, a.scale * b_scale, L);
+    Batch prod(e, B, 3, L, a.scale * b_scale), lin(e, B, 2, L, prod.scale);
+    ckks_view va = a.view(), vp = prod.view(), vl = lin.view();
     check(ckks_multiply(e->ctx, &va, &vb, &vp, nullptr));
     check(ckks_relinearize(e->ctx, &vp, rk.s->keys.at(0)->p, &vl, nullptr));
     Batch mult(e, B, 2, L - 1, prod.scale / (double)e->primes[L - 1]);
@@ -181,6 +181,11 @@ inline Batch dot_product_batch(const Batch &a, const Poly &b, int size, const se
     }
     mult.scale = std::pow(2.0, (int)std::log2(mult.scale));
     return mult;
+}
+
+inline Batch dot_product_batch(const Batch &a, const Poly &b, int size, const seal::RelinKeys &rk, const seal::GaloisKeys &gk) {
+    if (!b.buf) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    return dot_product_batch(a, b.view(), b.scale, size, rk, gk);
 }
 
 // one-hot masks e_0..e_{count-1} (length `length`), encoded as one batch at `limbs`
@@ -229,6 +234,24 @@ inline seal::Ciphertext predict_cipher_weights(const std::vector<seal::Ciphertex
     return Horner_cipher(lintransf_vec, degree, coeffs, ckks_encoder, scale, evaluator, encryptor, relin_keys, params);
 }
 
+// the tail of update_weights (logistic_regression_ckks.cpp:326-342, repair R3): weights - learning_rate / R * gradient
+inline seal::Ciphertext apply_gradient(seal::Ciphertext gradient, const seal::Ciphertext &weights, double learning_rate,
+                                       int num_observations, double scale, seal::Evaluator &evaluator, seal::CKKSEncoder &ckks_encoder) {
+    seal::Plaintext N_pt;
+    ckks_encoder.encode(learning_rate / num_observations, scale, N_pt);                          // :330-333
+    evaluator.mod_switch_to_inplace(N_pt, gradient.parms_id());
+    evaluator.multiply_plain_inplace(gradient, N_pt);
+    evaluator.rescale_to_next_inplace(gradient);                                                 // R3
+    gradient.scale() = std::pow(2.0, (int)std::log2(gradient.scale()));
+    seal::Ciphertext w_low = weights;
+    evaluator.mod_switch_to_inplace(w_low, gradient.parms_id());                                 // R3
+    w_low.scale() = gradient.scale();
+    seal::Ciphertext new_weights;
+    evaluator.sub(gradient, w_low, new_weights);                                                 // :341
+    evaluator.negate_inplace(new_weights);                                                       // :342
+    return new_weights;
+}
+
 // logistic_regression_ckks.cpp:269-345 -- weights - learning_rate / R * X^T (sigmoid(X w) - y), with repair R3
 inline seal::Ciphertext update_weights(const std::vector<seal::Ciphertext> &features, const std::vector<seal::Ciphertext> &features_T,
                                        seal::Ciphertext labels, const seal::Ciphertext &weights, float learning_rate,
@@ -247,19 +270,93 @@ inline seal::Ciphertext update_weights(const std::vector<seal::Ciphertext> &feat
     detail::Batch grads = detail::dot_product_batch(cols, pred_labels.poly(), num_observations, relin_keys, gal_keys);
     detail::Batch masks = detail::one_hot_masks(cols.e, num_weights, num_weights, scale, grads.limbs);   // :305-308
     seal::Ciphertext gradient = detail::masked_sum(grads, masks, evaluator);
-    seal::Plaintext N_pt;
-    ckks_encoder.encode((double)learning_rate / num_observations, scale, N_pt);                  // :330-333
-    evaluator.mod_switch_to_inplace(N_pt, gradient.parms_id());
-    evaluator.multiply_plain_inplace(gradient, N_pt);
-    evaluator.rescale_to_next_inplace(gradient);                                                 // R3
-    gradient.scale() = std::pow(2.0, (int)std::log2(gradient.scale()));
-    seal::Ciphertext w_low = weights;
-    evaluator.mod_switch_to_inplace(w_low, gradient.parms_id());                                 // R3
-    w_low.scale() = gradient.scale();
-    seal::Ciphertext new_weights;
-    evaluator.sub(gradient, w_low, new_weights);                                                 // :341
-    evaluator.negate_inplace(new_weights);                                                       // :342
-    return new_weights;
+    return apply_gradient(gradient, weights, learning_rate, num_observations, scale, evaluator, ckks_encoder);
+}
+
+// ---- config 5 (BASELINE.json): 8 features x 32768 samples do not fit the one-ciphertext-per-row layout (the mask
+// would be longer than the slot count), so samples are held as mini-batches of B <= slots/2 samples, each C column
+// ciphertexts; the weights are supplied as C broadcast ciphertexts.  Mini-batches are the multi-GPU sharding unit.
+struct ColumnLayout {
+    int R, C, B, M;
+    std::size_t slots;
+    ColumnLayout(int rows, int cols, int batch, std::size_t slot_count) : R(rows), C(cols), B(batch), M(rows / batch), slots(slot_count) {
+        if (R % B || (std::size_t)(2 * B) > slots) throw std::invalid_argument("B must divide R and 2B must fit in N/2 slots");
+    }
+    // entry m*C + j = feature j of mini-batch m
+    std::vector<double> column(const std::vector<std::vector<double>> &X, int m, int j) const {
+        std::vector<double> v(slots, 0.0);
+        for (int i = 0; i < B; i++) v[i] = X[(std::size_t)m * B + i][j];
+        return v;
+    }
+    std::vector<double> labels(const std::vector<double> &y, int m) const {
+        std::vector<double> v(slots, 0.0);
+        for (int i = 0; i < B; i++) v[i] = y[(std::size_t)m * B + i];
+        return v;
+    }
+};
+
+// One pass of the gradient loop over M mini-batches (the evaluator sequence of lr.py:column_epoch_gradient):
+// per mini-batch z = sum_j multiply(col_j, w_j), relinearize, rescale, sigmoid polynomial, sub labels; then, per
+// (mini-batch, feature), the reference's cipher_dot_product over B slots -- all M*C chains in lock-step -- the one-hot
+// mask e_j, add_many over everything, rescale.  Slot j of the result = sum_i x_ij (sigmoid(x_i . w) - y_i).
+inline seal::Ciphertext column_epoch_gradient(const std::vector<seal::Ciphertext> &cols, const std::vector<seal::Ciphertext> &labels,
+                                              const std::vector<seal::Ciphertext> &w_bcast, int B, double scale,
+                                              seal::Evaluator &evaluator, seal::CKKSEncoder &ckks_encoder,
+                                              const seal::GaloisKeys &gal_keys, const seal::RelinKeys &relin_keys,
+                                              seal::Encryptor &encryptor, const seal::EncryptionParameters &params, int degree = 7,
+                                              bool tree = true) {
+    const int C = (int)w_bcast.size(), M = (int)labels.size();
+    if (C < 1 || M < 1 || (int)cols.size() != M * C) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+    detail::Batch colb = detail::gather(cols), wb = detail::gather(w_bcast);
+    const auto &e = colb.e;
+    const int L = colb.limbs;
+    if (wb.limbs != L) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+    if (!relin_keys.s || !relin_keys.s->keys.count(0)) throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+    detail::scale_ok(*e, colb.scale * wb.scale, L);
+    // z_m = sum_j col_{m,j} x w_j: the fused multiply + add_many over the C features of each mini-batch
+    detail::Batch z3(e, M, 3, L, colb.scale * wb.scale), z2(e, M, 2, L, z3.scale), z(e, M, 2, L - 1, z3.scale / (double)e->primes[L - 1]);
+    for (int m = 0; m < M; m++) {
+        ckks_view va = colb.view(), vw = wb.view(), vo = z3.view();
+        va.data += (std::size_t)m * C * colb.entry_words();
+        va.batch = C;
+        vo.data += (std::size_t)m * z3.entry_words();
+        vo.batch = 1;
+        detail::check(ckks_multiply_sum(e->ctx, &va, &vw, &vo, nullptr));
+    }
+    ckks_view v3 = z3.view(), v2 = z2.view(), vz = z.view();
+    detail::check(ckks_relinearize(e->ctx, &v3, relin_keys.s->keys.at(0)->p, &v2, nullptr));
+    detail::check(ckks_rescale(e->ctx, &v2, &vz, nullptr));
+    z.scale = std::pow(2.0, (int)std::log2(z.scale));
+    // sigmoid polynomial and label subtraction per mini-batch (a handful of sequential ops each)
+    std::vector<double> coeffs = sigmoid_coeffs(degree);
+    std::vector<seal::Ciphertext> pred_labels(M);
+    for (int m = 0; m < M; m++) {
+        seal::Ciphertext zm;
+        z.get(m, zm.poly());
+        seal::Ciphertext pred = tree ? Tree_cipher(zm, degree, scale, coeffs, ckks_encoder, evaluator, encryptor, relin_keys, params)
+                                     : Horner_cipher(zm, degree, coeffs, ckks_encoder, scale, evaluator, encryptor, relin_keys, params);
+        seal::Ciphertext lab = labels[m];
+        evaluator.mod_switch_to_inplace(lab, pred.parms_id());
+        pred.scale() = lab.scale();
+        evaluator.sub(pred, lab, pred_labels[m]);
+    }
+    const int Lg = (int)pred_labels[0].coeff_mod_count();
+    detail::Batch colv = detail::gather_at(cols, Lg);
+    detail::Batch pl(e, M * C, 2, Lg, pred_labels[0].scale());              // entry m*C + j = pred_labels[m]
+    for (int m = 0; m < M; m++)
+        for (int j = 0; j < C; j++) pl.put(m * C + j, pred_labels[m].poly());
+    detail::Batch grads = detail::dot_product_batch(colv, pl.view(), pl.scale, B, relin_keys, gal_keys);
+    // masks e_j for every (m, j)
+    std::vector<double> mv((std::size_t)M * C * C, 0.0);
+    for (int m = 0; m < M; m++)
+        for (int j = 0; j < C; j++) mv[((std::size_t)m * C + j) * C + j] = 1.0;
+    detail::DevBuf vals(e, mv.size());
+    detail::check(ckks_upload(e->ctx, vals.p, mv.data(), mv.size() * 8, nullptr));
+    detail::check(ckks_stream_sync(e->ctx, nullptr));
+    detail::Batch masks(e, M * C, 1, grads.limbs, scale);
+    ckks_view vm = masks.view();
+    detail::check(ckks_encode(e->ctx, reinterpret_cast<const double *>(vals.p), C, scale, &vm, nullptr));
+    return detail::masked_sum(grads, masks, evaluator);
 }
 
 // logistic_regression_ckks.cpp:348-385 -- `iters` training iterations; the weights are refreshed after each one

@@ -24,3 +24,6 @@ echo "built matmul_driver"
 g++ -std=c++17 -O2 -Wall -I "$ROOT/include" -I "$PKG/include" "$ROOT/tests/cpp/lr_driver.cpp" -o "$OUT/lr_driver" \
     "$PKG/libckks_b200.so" -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../../../seal-fyp-logistic-regression_b200'
 echo "built lr_driver"
+g++ -std=c++17 -O2 -Wall -I "$ROOT/include" -I "$PKG/include" "$ROOT/tests/cpp/epoch_driver.cpp" -o "$OUT/epoch_driver" \
+    "$PKG/libckks_b200.so" -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../../../seal-fyp-logistic-regression_b200'
+echo "built epoch_driver"

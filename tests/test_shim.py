@@ -197,3 +197,21 @@ def test_shim_fails_loudly_without_gpu(pkg, tmp_path):
         pytest.skip("a CUDA device is present")
     res = subprocess.run([_build_host_checks(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 3 and "no CUDA device" in res.stdout, res.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_column_layout_epoch_matches_plaintext(pkg, tmp_path):
+    """tests/cpp/epoch_driver.cpp: the headline workload's op sequence (config 5: column layout, degree-7 tree
+    sigmoid, per-feature cipher_dot_product chains in lock-step) driven from C++ through
+    b200::column_epoch_gradient / apply_gradient, at a reduced size (64 samples, mini-batches of 16)"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    exe = os.path.join(REF_BUILD, "epoch_driver")
+    if not os.path.exists(exe):
+        exe = str(tmp_path / "epoch_driver")
+        res = subprocess.run(["g++", "-std=c++17", "-O2"] + INC + [os.path.join(ROOT, "tests", "cpp", "epoch_driver.cpp"), "-o", exe, LIB,
+                              "-Wl,-rpath," + os.path.dirname(LIB)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert res.returncode == 0, res.stdout[-3000:]
+    res = subprocess.run([exe, "64", "16", "1"], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "EPOCH OK" in res.stdout, res.stdout[-2000:]
