@@ -134,7 +134,10 @@ int ckks_apply_galois(ckks_ctx *ctx, const ckks_view *in, uint64_t galois_elt, c
 /* util::steps_to_galois_elt; returns 0 for |steps| >= N/2 ("step count too large") */
 uint64_t ckks_galois_elt_from_step(const ckks_ctx *ctx, int steps);
 
-/* key registry = SEAL RelinKeys + GaloisKeys (device pointers are borrowed, not copied) */
+/* key registry = SEAL RelinKeys + GaloisKeys.  Registering a key captures its contents: the engine keeps a private
+ * copy in the tile layout its inner-product kernels read fastest, and every entry point that is later given the
+ * same pointer (ckks_relinearize, ckks_apply_galois, the keyset-based calls) uses that copy.  The caller's buffer
+ * must stay allocated and unchanged while a keyset references it; register it again after changing it. */
 int ckks_keyset_create(ckks_ctx *ctx, ckks_keyset **out);
 void ckks_keyset_destroy(ckks_keyset *ks);
 int ckks_keyset_set_relin(ckks_keyset *ks, const uint64_t *rlk);

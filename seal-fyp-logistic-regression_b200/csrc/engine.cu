@@ -68,6 +68,12 @@ struct ckks_ctx {
     void *d_fp = nullptr, *d_twfd = nullptr, *d_twid = nullptr;
     std::unordered_map<uint64_t, uint32_t *> perms;
     bool pool_ready = false;
+    struct TiledKey {
+        u64 *copy = nullptr;
+        int refs = 0;
+    };
+    std::vector<struct ckks_keyset *> keysets;                   // live key registries (orphaned when the context goes first)
+    std::unordered_map<const uint64_t *, TiledKey> tiled_keys;   // registered key (caller's pointer) -> engine-owned tiled copy
     uint32_t *d_kidx = nullptr;                 // encoder: slot i -> DFT position (3^i mod 2N - 1)/2
     std::vector<HalfDigits> half_digits;        // decoder: mixed-radix digits of (Q_L - 1)/2, index L
     u64 *ws = nullptr;
@@ -181,6 +187,8 @@ extern "C" void ckks_ctx_destroy(ckks_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto &kv : c->perms) cudaFree(kv.second);
+    for (auto &kv : c->tiled_keys) cudaFree(kv.second.copy);
+    for (ckks_keyset *ks : c->keysets) ks->ctx = nullptr;
     cudaFree(c->d_kidx);
     for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
     if (c->chain_stream) cudaStreamDestroy(c->chain_stream);
@@ -601,13 +609,24 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
     return CKKS_OK;
 }
 
-static KsRoute uniform_route(const ckks_view *in, const ckks_view *out, const uint32_t *perm, const uint64_t *key) {
+// the engine-owned tiled copy of a registered key, or the caller's buffer (standard layout) for an unregistered one
+static const u64 *resolve_key(const ckks_ctx *c, const uint64_t *key, int *tiled) {
+    auto it = c->tiled_keys.find(key);
+    if (it == c->tiled_keys.end()) {
+        *tiled = 0;
+        return (const u64 *)key;
+    }
+    *tiled = 1;
+    return it->second.copy;
+}
+
+static KsRoute uniform_route(const ckks_ctx *c, const ckks_view *in, const ckks_view *out, const uint32_t *perm, const uint64_t *key) {
     KsRoute rt{};
     rt.v[0] = dv(in);
     rt.v[1] = dv(out);
     rt.v[2] = dv(out);
     rt.perm0 = perm;
-    rt.key0 = (const u64 *)key;
+    rt.key0 = resolve_key(c, key, &rt.key_tiled);
     return rt;
 }
 
@@ -649,7 +668,7 @@ extern "C" int ckks_relinearize(ckks_ctx *c, const ckks_view *in, const uint64_t
     if (out->data == in->data && (out->poly_stride != in->poly_stride || out->batch_stride != in->batch_stride))
         return fail(CKKS_ERR_INVALID, "relinearize: in-place only with identical strides");
     CU(cudaSetDevice(c->device));
-    return keyswitch_lanes(c, 1, in->limbs, in->batch, uniform_route(in, out, nullptr, rlk), (cudaStream_t)s);
+    return keyswitch_lanes(c, 1, in->limbs, in->batch, uniform_route(c, in, out, nullptr, rlk), (cudaStream_t)s);
 }
 
 extern "C" int ckks_apply_galois(ckks_ctx *c, const ckks_view *in, uint64_t g, const uint64_t *gk, const ckks_view *out, ckks_stream s) {
@@ -663,21 +682,64 @@ extern "C" int ckks_apply_galois(ckks_ctx *c, const ckks_view *in, uint64_t g, c
     const uint32_t *perm = nullptr;
     if ((rc = get_perm(c, g, &perm))) return rc;
     CU(cudaSetDevice(c->device));
-    return keyswitch_lanes(c, 2, in->limbs, in->batch, uniform_route(in, out, perm, gk), (cudaStream_t)s);
+    return keyswitch_lanes(c, 2, in->limbs, in->batch, uniform_route(c, in, out, perm, gk), (cudaStream_t)s);
 }
 
 extern "C" int ckks_keyset_create(ckks_ctx *c, ckks_keyset **out) {
     if (!c || !out) return fail(CKKS_ERR_INVALID, "null argument");
     *out = new ckks_keyset{c};
+    c->keysets.push_back(*out);
     return CKKS_OK;
 }
+// Registration captures the key: a private copy in the tiled layout the inner-product kernels read fastest
+// (k_retile_key).  The copy lives while some keyset references the caller's pointer; entry points that receive
+// that pointer directly (ckks_relinearize, ckks_apply_galois) find it through the context's registry.
+static int register_key(ckks_ctx *c, const uint64_t *key) {
+    if (!key) return fail(CKKS_ERR_INVALID, "null key");
+    if ((uintptr_t)key & 15) return fail(CKKS_ERR_INVALID, "key must be 16-byte aligned");
+    CU(cudaSetDevice(c->device));
+    ckks_ctx::TiledKey &t = c->tiled_keys[key];
+    const size_t words = ckks_ksk_words(c);
+    if (!t.copy && cudaMalloc((void **)&t.copy, words * 8) != cudaSuccess) {
+        cudaGetLastError();
+        c->tiled_keys.erase(key);
+        return fail(CKKS_ERR_NOMEM, "device allocation failed");
+    }
+    t.refs++;
+    k_retile_key<<<(unsigned)(words / NTT_TILE), NTT_THREADS>>>((const u64 *)key, t.copy);   // (re)capture the contents
+    LAUNCH_CHECK(c);
+    return CKKS_OK;
+}
+static void unregister_key(ckks_ctx *c, const uint64_t *key) {
+    auto it = c->tiled_keys.find(key);
+    if (it == c->tiled_keys.end() || --it->second.refs > 0) return;
+    cudaSetDevice(c->device);
+    cudaFree(it->second.copy);   // synchronises: no kernel still reads the copy
+    c->tiled_keys.erase(it);
+    for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);   // cached graphs may hold the freed address
+    c->chain_graphs.clear();
+}
+
 extern "C" void ckks_keyset_destroy(ckks_keyset *ks) {
     if (!ks) return;
+    if (ks->ctx) {   // (a context destroyed before its keysets has already released the copies)
+        if (ks->relin) unregister_key(ks->ctx, ks->relin);
+        for (auto &kv : ks->galois) unregister_key(ks->ctx, kv.second);
+        auto &v = ks->ctx->keysets;
+        for (size_t i = 0; i < v.size(); i++)
+            if (v[i] == ks) {
+                v.erase(v.begin() + i);
+                break;
+            }
+    }
     cudaFree((void *)ks->d_perm_tab);
     cudaFree((void *)ks->d_key_tab);
     delete ks;
 }
 extern "C" int ckks_keyset_set_relin(ckks_keyset *ks, const uint64_t *rlk) {
+    int rc = register_key(ks->ctx, rlk);
+    if (rc) return rc;
+    if (ks->relin) unregister_key(ks->ctx, ks->relin);
     ks->relin = rlk;
     return CKKS_OK;
 }
@@ -685,6 +747,9 @@ extern "C" int ckks_keyset_set_galois(ckks_keyset *ks, uint64_t g, const uint64_
     const uint32_t *perm = nullptr;
     int rc = get_perm(ks->ctx, g, &perm);  // build the permutation table now (not capturable later)
     if (rc) return rc;
+    if ((rc = register_key(ks->ctx, gk))) return rc;
+    auto old = ks->galois.find(g);
+    if (old != ks->galois.end()) unregister_key(ks->ctx, old->second);
     ks->galois[g] = gk;
     if (!ks->slot_of.count(g)) {
         ks->slot_of[g] = (int)ks->slot_elt.size();
@@ -766,7 +831,7 @@ extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const c
         vd.data += (uint64_t)off * vd.batch_stride;
         va.data += (uint64_t)off * va.batch_stride;
         vs.batch = vd.batch = va.batch = cnt;
-        KsRoute rt = uniform_route(&vs, &vd, perm, it->second);
+        KsRoute rt = uniform_route(c, &vs, &vd, perm, it->second);
         rt.accv = dv(&va);
         rt.has_acc = 1;
         return keyswitch(c, 2, L, cnt, rt, st, chained, li);
@@ -790,7 +855,8 @@ extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const c
             const int off = split[li], cnt = split[li + 1] - split[li];
             if ((rc = ensure_lane(c, li, ks_words_per_ct(c, L) * 8 * (size_t)ks_chunk(c, cnt, L)))) return rc;
             ckks_ctx::Lane &ln = c->lane[li];
-            std::vector<uint64_t> key = {(uint64_t)a->data, (uint64_t)b->data, (uint64_t)acc->data, (uint64_t)it->second, g,
+            int key_tiled = 0;
+            std::vector<uint64_t> key = {(uint64_t)a->data, (uint64_t)b->data, (uint64_t)acc->data, (uint64_t)resolve_key(c, it->second, &key_tiled), g,
                                          (uint64_t)L, (uint64_t)off, (uint64_t)cnt, a->batch_stride, a->poly_stride, b->batch_stride,
                                          b->poly_stride, acc->batch_stride, acc->poly_stride, (uint64_t)ln.ws, (uint64_t)c->t.round_half};
             auto gi = c->chain_graphs.find(key);
@@ -861,7 +927,8 @@ static int sync_key_tables(ckks_keyset *ks) {
     for (int i = 0; i < n; i++) {
         int rc = get_perm(c, ks->slot_elt[i], &hp[i]);
         if (rc) return rc;
-        hk[i] = (const u64 *)ks->galois.at(ks->slot_elt[i]);
+        int tiled = 0;
+        hk[i] = resolve_key(c, ks->galois.at(ks->slot_elt[i]), &tiled);   // registered keys: always the tiled copy
     }
     if (n) {
         CU(cudaMemcpy((void *)ks->d_perm_tab, hp.data(), sizeof(void *) * n, cudaMemcpyHostToDevice));
@@ -968,6 +1035,7 @@ extern "C" int ckks_rotate_plan(ckks_ctx *c, const ckks_rotplan *p, const ckks_v
     rt.v[2] = need_scratch ? dv(scratch) : dv(out);
     rt.perm_tab = p->ks->d_perm_tab;
     rt.key_tab = p->ks->d_key_tab;
+    rt.key_tiled = 1;
     for (int b : p->zero_entries) {   // rotate by 0: SEAL returns the input unchanged
         DView src = rt.v[0], dst = rt.v[1];
         src.data += (u64)b * src.bs;

@@ -110,6 +110,7 @@ struct KsRoute {
     int tgt_poly;                      // polynomial that is key-switched (2 relin, 1 Galois)
     DView accv;                        // optional: accv[entry] += result (rotate-and-sum chains)
     int has_acc;
+    int key_tiled;                     // keys are engine-owned copies in the thread-major tile layout (k_retile_key)
 };
 __device__ __forceinline__ KsSel route_sel(const KsRoute &r, int z) {
     if (r.sel) return r.sel[r.b0 + z];
@@ -403,11 +404,14 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
             fwd_row_pass<LOGN>(x, tw, m, t0, stage[slot]);
             slot ^= 1;
         }
-        const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
-        const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+        // standard layout: the thread's 8 words are contiguous (4 x 16 B, 64 B apart between threads: every warp
+        // load touches 16 lines); tiled layout: word pair v of thread t sits at 512 v + 2 t (4 lines per warp load)
+        const int koff = rt.key_tiled ? 2 * threadIdx.x : 8 * threadIdx.x, kstep = rt.key_tiled ? 256 : 1;
+        const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + koff);
+        const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + koff);
 #pragma unroll
         for (int v = 0; v < 4; v++) {
-            ulonglong2 a = __ldg(k0 + v), c = __ldg(k1 + v);
+            ulonglong2 a = __ldg(k0 + kstep * v), c = __ldg(k1 + kstep * v);
             mac128(lo0[2 * v], hi0[2 * v], x[2 * v], a.x);
             mac128(lo0[2 * v + 1], hi0[2 * v + 1], x[2 * v + 1], a.y);
             mac128(lo1[2 * v], hi1[2 * v], x[2 * v], c.x);
@@ -490,11 +494,14 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsR
             fwd_row_pass_fp<LOGN>(x, tw, f, t0, as_fp(stage[slot]));   // lazy, |x| < 32p
             slot ^= 1;
         }
-        const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
-        const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+        // standard layout: the thread's 8 words are contiguous (4 x 16 B, 64 B apart between threads: every warp
+        // load touches 16 lines); tiled layout: word pair v of thread t sits at 512 v + 2 t (4 lines per warp load)
+        const int koff = rt.key_tiled ? 2 * threadIdx.x : 8 * threadIdx.x, kstep = rt.key_tiled ? 256 : 1;
+        const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + koff);
+        const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + koff);
 #pragma unroll
         for (int v = 0; v < 4; v++) {
-            ulonglong2 a = __ldg(k0 + v), c = __ldg(k1 + v);
+            ulonglong2 a = __ldg(k0 + kstep * v), c = __ldg(k1 + kstep * v);
             a0[2 * v] = __dadd_rn(a0[2 * v], fp_mulmod(x[2 * v], fp_from_u64(a.x), f));
             a0[2 * v + 1] = __dadd_rn(a0[2 * v + 1], fp_mulmod(x[2 * v + 1], fp_from_u64(a.y), f));
             a1[2 * v] = __dadd_rn(a1[2 * v], fp_mulmod(x[2 * v], fp_from_u64(c.x), f));
@@ -628,6 +635,16 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *T2, DV
         for (int e = 0; e < 8; e++) av[e] = addmod(av[e], x[e], m.p);
         store8(ap, av);
     }
+}
+
+// Key-switch keys are static: at registration the engine makes a private copy in which, inside every 2048-word
+// tile, word pair v (0..3) of thread t (0..255) is stored at 512 v + 2 t instead of 8 t + 2 v, so that the
+// inner-product kernels' 16-byte key loads are contiguous across a warp.
+__global__ void k_retile_key(const u64 *src, u64 *dst) {
+    const size_t base = (size_t)blockIdx.x * NTT_TILE;
+    const ulonglong2 *s = reinterpret_cast<const ulonglong2 *>(src + base + 8 * threadIdx.x);
+#pragma unroll
+    for (int v = 0; v < 4; v++) *reinterpret_cast<ulonglong2 *>(dst + base + 512 * v + 2 * threadIdx.x) = s[v];
 }
 
 // =============================================================================== element-wise
