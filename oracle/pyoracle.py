@@ -22,12 +22,45 @@ _f64p = C.POINTER(C.c_double)
 _intp = C.POINTER(C.c_int)
 
 
+def _host_stamp():
+    """content hash of the oracle sources + the host CPU's feature flags: the library is compiled
+    -march=native, so a copy built on another machine (this repository travels to the GPU box with its
+    built artefacts) must be rebuilt rather than trusted by modification time"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("ckks_oracle.c", "ckks_oracle.h", "Makefile"):
+        with open(os.path.join(_HERE, f), "rb") as fh:
+            h.update(fh.read())
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags") or line.startswith("model name"):
+                    h.update(line.encode())
+                    if line.startswith("flags"):
+                        break
+    except OSError:
+        pass
+    return h.hexdigest()
+
+
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("ckks_oracle.c", "ckks_oracle.h")]
-    if (not force and os.path.exists(_LIB_PATH)
-            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
-        return _LIB_PATH
-    subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    stamp_path = _LIB_PATH + ".hoststamp"
+    stamp = _host_stamp()
+    if not force and os.path.exists(_LIB_PATH) and os.path.exists(stamp_path):
+        with open(stamp_path) as fh:
+            if fh.read().strip() == stamp:
+                return _LIB_PATH
+    import fcntl
+    with open(_LIB_PATH + ".lock", "w") as lock:          # one builder at a time (torchrun ranks, xdist workers)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(_LIB_PATH) and os.path.exists(stamp_path) and open(stamp_path).read().strip() == stamp:
+                return _LIB_PATH
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libckks_oracle.so"])
+            with open(stamp_path, "w") as fh:
+                fh.write(stamp + "\n")
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _LIB_PATH
 
 

@@ -210,3 +210,59 @@ def update_weights(E, features, features_T, labels, weights, lr, scale, coeffs, 
     w_low = E.mod_switch_to(weights, gradient.limbs)
     w_low.scale = gradient.scale
     return E.negate(E.sub(gradient, w_low))
+
+
+def linear_transform_ciphermatrix_plainvector(E, pt_rotations, ct_diags):
+    """helper.h:265-278: sum_i multiply_plain(ct_diag_i, pt_rot_i)"""
+    return E.add_many([E.multiply_plain(c, p) for c, p in zip(ct_diags, pt_rotations)])
+
+
+def c_matrix_decode(E, matrix, d, scale, encode):
+    """helper.h:325-360: row i = rotate(multiply_plain(matrix, ones on [i*d, (i+1)*d)), i*d)"""
+    rows = []
+    for i in range(d):
+        mask = np.zeros(d * d)
+        mask[i * d:(i + 1) * d] = 1.0
+        row = E.multiply_plain(matrix, encode(mask, scale, matrix.limbs))
+        rows.append(row if i == 0 else E.rotate(row, i * d))
+    return rows
+
+
+def column_epoch_gradient(E, cols, labels, w_bcast, C, B, scale, coeffs, encode, encrypt_for_batch, method="tree"):
+    """Sequential restatement of the product's column-layout epoch (lr.py column_epoch_gradient): per
+    mini-batch m the prediction z = sum_j multiply(col_j, w_j), relinearize, rescale, forced scale, the
+    sigmoid polynomial (logistic_regression_ckks.cpp:55-137 / :139-205), sub labels (:286-288); per
+    feature j the reference's cipher_dot_product over B slots and the one-hot mask e_j (:295-311);
+    add_many over every (m, j); rescale; forced scale (:316-323).
+    cols: list of M*C OCt (entry m*C + j); labels: list of M; w_bcast: list of C.
+    encrypt_for_batch(m) returns the encrypt callable of mini-batch m (the batched product path draws
+    one fresh encryption per polynomial call and shares it across the batch)."""
+    M = len(labels)
+    poly = tree_cipher if method == "tree" else horner_cipher
+    grads = []
+    for m in range(M):
+        prods = [E.multiply(cols[m * C + j], w_bcast[j]) for j in range(C)]
+        z = E.rescale(E.relinearize(E.add_many(prods)))
+        z.scale = pow2(z.scale)
+        pred = poly(E, z, coeffs, scale, encode, encrypt_for_batch(m))
+        lab = E.mod_switch_to(labels[m], pred.limbs)
+        pred.scale = lab.scale
+        pred_labels = E.sub(pred, lab)
+        for j in range(C):
+            col = E.mod_switch_to(cols[m * C + j], pred_labels.limbs)
+            g = cipher_dot_product(E, col, pred_labels, B)
+            mask = np.zeros(C)
+            mask[j] = 1.0
+            grads.append(E.multiply_plain(g, encode(mask, scale, g.limbs)))
+    gradient = E.rescale(E.add_many(grads))
+    gradient.scale = pow2(gradient.scale)
+    return gradient
+
+
+def apply_gradient(E, gradient, weights, lr, R, scale, encode):
+    """tail of update_weights (logistic_regression_ckks.cpp:326-342, repair R3)"""
+    g = E.rescale(E.multiply_plain(gradient, encode(float(lr / R), scale, gradient.limbs)))
+    g.scale = pow2(g.scale)
+    w_low = E.mod_switch_to(weights, g.limbs)
+    w_low.scale = g.scale
+    return E.negate(E.sub(g, w_low))
