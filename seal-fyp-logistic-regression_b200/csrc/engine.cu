@@ -93,6 +93,8 @@ struct ckks_ctx {
         cudaEvent_t fork = nullptr, join = nullptr, begin = nullptr, end = nullptr;
     } lane[4];
     int chain_lanes = 2;
+    int fuse = 1;              // fused column passes / INTT-in-MAC (CKKS_FUSE=0 selects the unfused round-1 pipeline)
+    int split1 = 0, split3 = 0; // forced nsplit of the fused column kernels (0 = heuristic)
     struct ChainGraph {
         cudaGraphExec_t exec;
         uint64_t launches;
@@ -179,6 +181,10 @@ extern "C" int ckks_ctx_create(int log_n, int n_primes, const uint64_t *primes, 
     c->t.twid = (const double *)c->d_twid;
     c->t.K = n_primes;
     c->t.round_half = 1;
+    if (const char *e = getenv("CKKS_FUSE")) c->fuse = atoi(e);
+    if (const char *e = getenv("CKKS_SPLIT1")) c->split1 = atoi(e);
+    if (const char *e = getenv("CKKS_SPLIT3")) c->split3 = atoi(e);
+    if (const char *e = getenv("CKKS_LANES")) c->chain_lanes = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
     *out = c;
     return CKKS_OK;
 }
@@ -530,6 +536,14 @@ static int get_perm(ckks_ctx *c, uint64_t g, const uint32_t **out) {
     return CKKS_OK;
 }
 
+// nsplit of the fused column kernels: one CTA per tile does every target prime when the launch already fills the
+// GPU (148 SMs x 4 resident CTAs); a small batch splits the targets over up to `maxsplit` CTAs per tile instead
+static int pick_split(int forced, int tiles, int maxsplit) {
+    int ns = forced > 0 ? forced : (tiles >= 592 ? 1 : (592 + tiles - 1) / tiles);
+    if (ns > maxsplit) ns = maxsplit;
+    return ns < 1 ? 1 : ns;
+}
+
 // Batched key switch over `nslots` launch slots.
 // mode 1: relinearize (target = poly 2 of the source, base = polys 0,1)
 // mode 2: Galois      (target = permuted poly 1, base = permuted poly 0)
@@ -547,7 +561,8 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
     rt.tgt_poly = mode == 1 ? 2 : 1;
     // output limbs by prime size: integer kernel for large primes, FP64 kernel for small ones
     JjList big{}, small{};
-    for (int jj = 0; jj <= L; jj++) {
+    const int fuse = c->fuse;
+    for (int jj = L; jj >= 0; jj--) {   // special-prime limb first: with the fused INTT its CTAs are the longest
         const int pj = jj == L ? K - 1 : jj;
         JjList &dst = (c->primes[pj] >> 41) == 0 ? small : big;
         dst.jj[dst.n++] = (signed char)jj;
@@ -568,10 +583,16 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         else if (mode == 2) k_ks_intt_row<LN, true><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(rt, D, L, c->t); \
         else k_ks_intt_row<LN, false><<<dim3(G::ROW_TILES, L, bc), NTT_THREADS, 0, st>>>(rt, D, L, c->t);       \
         LAUNCH_CHECK(c);                                                                                                \
-        launch_pdl(k_inv_col<LN, false>, dim3(G::COL_TILES, L, bc), st, dD, dD, L, 0, c->t);                    \
-        LAUNCH_CHECK(c);                                                                                                \
-        launch_pdl(k_ks_modup_col<LN>, dim3(G::COL_TILES, L *(L + 1), bc), st, D, T1, L, c->t);                 \
-        LAUNCH_CHECK(c);                                                                                                \
+        if (fuse) {                                                                                                     \
+            const int ns1 = pick_split(c->split1, G::COL_TILES * L * bc, L);                                            \
+            launch_pdl(k_ks_invcol_modup<LN>, dim3(G::COL_TILES, L * ns1, bc), st, D, T1, L, ns1, c->t);                \
+            LAUNCH_CHECK(c);                                                                                            \
+        } else {                                                                                                        \
+            launch_pdl(k_inv_col<LN, false>, dim3(G::COL_TILES, L, bc), st, dD, dD, L, 0, c->t);                \
+            LAUNCH_CHECK(c);                                                                                            \
+            launch_pdl(k_ks_modup_col<LN>, dim3(G::COL_TILES, L *(L + 1), bc), st, D, T1, L, c->t);             \
+            LAUNCH_CHECK(c);                                                                                            \
+        }                                                                                                               \
         /* the FP64 inner product (small-prime limbs) is independent of the integer one and of the special-prime  \
            INTT that follows: fork it onto the side stream, join before the last kernel reads its output */       \
         cudaStream_t sfp = (big.n && small.n) ? ln.side : st;                                                          \
@@ -580,24 +601,30 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
                 CU(cudaEventRecord(ln.fork, st));                                                                       \
                 CU(cudaStreamWaitEvent(sfp, ln.fork, 0));                                                               \
             }                                                                                                           \
-            if (mode == 2) k_ks_mac_fp<LN, true><<<dim3(G::ROW_TILES, small.n, bc), NTT_THREADS, 0, sfp>>>(T1, rt, ACC, L, small, c->t); \
-            else k_ks_mac_fp<LN, false><<<dim3(G::ROW_TILES, small.n, bc), NTT_THREADS, 0, sfp>>>(T1, rt, ACC, L, small, c->t); \
+            if (mode == 2) k_ks_mac_fp<LN, true><<<dim3(G::ROW_TILES, small.n, bc), NTT_THREADS, 0, sfp>>>(T1, rt, ACC, L, small, fuse, c->t); \
+            else k_ks_mac_fp<LN, false><<<dim3(G::ROW_TILES, small.n, bc), NTT_THREADS, 0, sfp>>>(T1, rt, ACC, L, small, fuse, c->t); \
             LAUNCH_CHECK(c);                                                                                            \
             if (sfp != st) CU(cudaEventRecord(ln.join, sfp));                                                           \
         }                                                                                                               \
         if (big.n) {                                                                                                    \
-            if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, c->t); \
-            else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, c->t);         \
+            if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, fuse, c->t); \
+            else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, fuse, c->t);   \
             LAUNCH_CHECK(c);                                                                                            \
         }                                                                                                               \
         /* a small special prime puts its limb on the side stream: the INTT below must wait for it */            \
         if (sfp != st && special_small) CU(cudaStreamWaitEvent(st, ln.join, 0));                                        \
-        launch_pdl(k_inv_row<LN>, dim3(G::ROW_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);               \
-        LAUNCH_CHECK(c);                                                                                                \
-        launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);         \
-        LAUNCH_CHECK(c);                                                                                                \
-        launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, L, 2 * bc), st, spec, T2, L, K - 1, c->t);              \
-        LAUNCH_CHECK(c);                                                                                                \
+        if (fuse) {                                                                                                     \
+            const int ns3 = pick_split(c->split3, G::COL_TILES * 2 * bc, L);                                            \
+            launch_pdl(k_md_invcol_fwdcol<LN>, dim3(G::COL_TILES, ns3, 2 * bc), st, spec, T2, L, K - 1, ns3, c->t);     \
+            LAUNCH_CHECK(c);                                                                                            \
+        } else {                                                                                                        \
+            launch_pdl(k_inv_row<LN>, dim3(G::ROW_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);           \
+            LAUNCH_CHECK(c);                                                                                            \
+            launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, 1, 2 * bc), st, spec, spec, 1, K - 1, c->t);     \
+            LAUNCH_CHECK(c);                                                                                            \
+            launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, L, 2 * bc), st, spec, T2, L, K - 1, c->t);          \
+            LAUNCH_CHECK(c);                                                                                            \
+        }                                                                                                               \
         if (sfp != st && !special_small) CU(cudaStreamWaitEvent(st, ln.join, 0));                                       \
         if (mode == 2) launch_pdl(k_md_fwd_row<LN, 2>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
         else launch_pdl(k_md_fwd_row<LN, 1>, dim3(G::ROW_TILES, L, 2 * bc), st, T2, minu, rt, 2, L, K - 1, c->t); \
@@ -706,7 +733,7 @@ static int register_key(ckks_ctx *c, const uint64_t *key) {
         return fail(CKKS_ERR_NOMEM, "device allocation failed");
     }
     t.refs++;
-    k_retile_key<<<(unsigned)(words / NTT_TILE), NTT_THREADS>>>((const u64 *)key, t.copy);   // (re)capture the contents
+    k_retile_key<<<(unsigned)(words / NTT_TILE), NTT_THREADS>>>((const u64 *)key, t.copy, c->log_n, c->t);   // (re)capture the contents
     LAUNCH_CHECK(c);
     return CKKS_OK;
 }
@@ -1106,10 +1133,16 @@ extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *o
         typedef NttGeo<LN> G;                                                                                     \
         k_inv_row<LN><<<dim3(G::ROW_TILES, S, bc), NTT_THREADS, 0, st>>>(last, dR, 1, Lo, c->t);                  \
         LAUNCH_CHECK(c);                                                                                          \
-        launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, S, bc), st, dR, dR, 1, Lo, c->t);              \
-        LAUNCH_CHECK(c);                                                                                          \
-        launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, Lo, bc * S), st, Rz, T2, Lo, Lo, c->t);           \
-        LAUNCH_CHECK(c);                                                                                          \
+        if (c->fuse) {                                                                                            \
+            const int ns3 = pick_split(c->split3, G::COL_TILES * S * bc, Lo);                                     \
+            launch_pdl(k_md_invcol_fwdcol<LN>, dim3(G::COL_TILES, ns3, bc * S), st, Rz, T2, Lo, Lo, ns3, c->t);   \
+            LAUNCH_CHECK(c);                                                                                      \
+        } else {                                                                                                  \
+            launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, S, bc), st, dR, dR, 1, Lo, c->t);          \
+            LAUNCH_CHECK(c);                                                                                      \
+            launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, Lo, bc * S), st, Rz, T2, Lo, Lo, c->t);       \
+            LAUNCH_CHECK(c);                                                                                      \
+        }                                                                                                         \
         launch_pdl(k_md_fwd_row<LN, 0>, dim3(G::ROW_TILES, Lo, bc * S), st, T2, src, rrt, S, Lo, Lo, c->t); \
         LAUNCH_CHECK(c);                                                                                          \
     }

@@ -334,6 +334,67 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *D, u
     for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
 }
 
+// (2+3) fused: inverse column pass of digit i (its row pass is in D) and, on the same 64 x 32 tile and
+// register layout, the mod-up column pass into every other prime -- the digit never returns to memory in
+// coefficient form (one launch and one D round trip less than k_inv_col + k_ks_modup_col).
+// grid: (COL_TILES, L * nsplit, batch); part p of a digit handles its targets p, p + nsplit, ...
+// (nsplit > 1 trades a repeated inverse pass for more CTAs when the batch is too small to fill the GPU).
+template <int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_ks_invcol_modup(const u64 *D, u64 *T1, int L, int nsplit, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[2][NTT_TILE];   // alternating exchange buffers: no barrier needed between passes
+    pdl_launch_dependents();
+    const int i = blockIdx.y / nsplit, part = blockIdx.y % nsplit, b = blockIdx.z;
+    const u64 *in = D + ((u64)b * L + i) * G::N;
+    const ModConst mi = load_mod(t, i);
+    const FpConst fi = t.fp[i];
+    const int c0 = blockIdx.x * 32;
+    u64 v[8];
+    pdl_wait();
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = in[col_fine_idx<LOGN>(c0, e)];
+    if (fi.ok != 0.0) {
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = bits_fp(v[e]);
+        inv_col_pass_fp<LOGN>(xd, t.twid + (size_t)i * G::N, fi, as_fp(smem[0]));
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = fp_to_canonical(xd[e], fi);
+    } else {
+        inv_col_pass<LOGN>(v, t.twi + (size_t)i * G::N, mi, smem[0]);
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = csub(csub(v[e], mi.p2), mi.p);
+    }
+    int buf = 1, cnt = 0;
+    for (int jj = 0; jj <= L; jj++) {
+        const int pj = jj == L ? t.K - 1 : jj;
+        if (pj == i) continue;   // that limb is taken directly from the NTT-form target
+        if ((cnt++ % nsplit) != part) continue;
+        const ModConst m = load_mod(t, pj);
+        const FpConst f = t.fp[pj];
+        // SEAL reduces the digit modulo q_j only when q_i > q_j; the transform itself accepts any value
+        // below 8 q_j, so the Barrett reduction is needed only for a much larger source prime
+        const bool need_reduce = mi.p >= m.p4;
+        u64 *out = T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N;
+        u64 x[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = need_reduce ? reduce64(v[e], m) : v[e];
+        if (f.ok != 0.0) {   // x < 4 q_j < 2^43: exact as doubles
+            double xd[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+            fwd_col_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, as_fp(smem[buf]));
+#pragma unroll
+            for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = fp_bits(xd[e]);
+        } else {
+            fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, smem[buf]);
+#pragma unroll
+            for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
+        }
+        buf ^= 1;
+    }
+}
+
 // (4) mod-up row pass fused with the key inner product: for output limb jj of ciphertext b,
 //     acc_k = sum_i NTT_pj(digit_i) (.) ksk[i][k][pj]     (k = 0,1), 128-bit lazy sums,
 // one Barrett reduction at the end.  Key limbs stream once from HBM, fully coalesced.
@@ -344,7 +405,7 @@ struct JjList {
     signed char jj[36];
 };
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, int fuse_inv, Tables t) {
     typedef NttGeo<LOGN> G;
     // TMA-staged input tiles of the current / next digit; the current one doubles as the exchange buffer
     __shared__ __align__(128) u64 stage[2][NTT_TILE];
@@ -418,6 +479,26 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
             mac128(lo1[2 * v + 1], hi1[2 * v + 1], x[2 * v + 1], c.y);
         }
     }
+    if (fuse_inv && jj == L) {
+        // special-prime limb: the accumulated tile is exactly the input tile of the mod-down INTT's row pass --
+        // run it here (k_inv_row fused), writing the strided-side result over the limb's slot in ACC
+        u64 *b0 = ACC + (((u64)b * 2 + 0) * (L + 1) + jj) * G::N + t0;
+        u64 *b1 = ACC + (((u64)b * 2 + 1) * (L + 1) + jj) * G::N + t0;
+        const tw_t *twi = t.twi + (size_t)pj * G::N;
+        u64 r[8];
+        __syncthreads();   // every thread is done with the exchange buffers of the last digit
+#pragma unroll
+        for (int e = 0; e < 8; e++) r[e] = barrett128(lo0[e], hi0[e], m);
+        inv_row_pass<LOGN>(r, twi, m, t0, stage[0]);
+#pragma unroll
+        for (int e = 0; e < 8; e++) b0[row_strided_li<LOGN>(e)] = r[e];
+#pragma unroll
+        for (int e = 0; e < 8; e++) r[e] = barrett128(lo1[e], hi1[e], m);
+        inv_row_pass<LOGN>(r, twi, m, t0, stage[1]);
+#pragma unroll
+        for (int e = 0; e < 8; e++) b1[row_strided_li<LOGN>(e)] = r[e];
+        return;
+    }
     u64 *o0 = ACC + (((u64)b * 2 + 0) * (L + 1) + jj) * G::N + t0 + 8 * threadIdx.x;
     u64 *o1 = ACC + (((u64)b * 2 + 1) * (L + 1) + jj) * G::N + t0 + 8 * threadIdx.x;
 #pragma unroll
@@ -435,7 +516,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
 // FP64 variant for output limbs with a small prime: transform, products and the running sums all
 // stay on the FP64 pipe (|sum| < 2p per term, at most 32 terms: exact), one canonicalisation at the end
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, int fuse_inv, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ __align__(128) u64 stage[2][NTT_TILE];   // TMA-staged tiles; the current one is also the exchange buffer
     __shared__ u64 bars[2];
@@ -502,11 +583,31 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsR
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             ulonglong2 a = __ldg(k0 + kstep * v), c = __ldg(k1 + kstep * v);
-            a0[2 * v] = __dadd_rn(a0[2 * v], fp_mulmod(x[2 * v], fp_from_u64(a.x), f));
-            a0[2 * v + 1] = __dadd_rn(a0[2 * v + 1], fp_mulmod(x[2 * v + 1], fp_from_u64(a.y), f));
-            a1[2 * v] = __dadd_rn(a1[2 * v], fp_mulmod(x[2 * v], fp_from_u64(c.x), f));
-            a1[2 * v + 1] = __dadd_rn(a1[2 * v + 1], fp_mulmod(x[2 * v + 1], fp_from_u64(c.y), f));
+            // engine-owned (tiled) key copies hold small-prime limbs as doubles already (k_retile_key)
+            const double kax = rt.key_tiled ? bits_fp(a.x) : fp_from_u64(a.x), kay = rt.key_tiled ? bits_fp(a.y) : fp_from_u64(a.y);
+            const double kcx = rt.key_tiled ? bits_fp(c.x) : fp_from_u64(c.x), kcy = rt.key_tiled ? bits_fp(c.y) : fp_from_u64(c.y);
+            a0[2 * v] = __dadd_rn(a0[2 * v], fp_mulmod(x[2 * v], kax, f));
+            a0[2 * v + 1] = __dadd_rn(a0[2 * v + 1], fp_mulmod(x[2 * v + 1], kay, f));
+            a1[2 * v] = __dadd_rn(a1[2 * v], fp_mulmod(x[2 * v], kcx, f));
+            a1[2 * v + 1] = __dadd_rn(a1[2 * v + 1], fp_mulmod(x[2 * v + 1], kcy, f));
         }
+    }
+    if (fuse_inv && jj == L) {   // small special prime: mod-down INTT row pass fused, as in k_ks_mac
+        u64 *b0 = ACC + (((u64)b * 2 + 0) * (L + 1) + jj) * G::N + t0;
+        u64 *b1 = ACC + (((u64)b * 2 + 1) * (L + 1) + jj) * G::N + t0;
+        const double *twi = t.twid + (size_t)pj * G::N;
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; e++) a0[e] = fp_reduce(a0[e], f);
+        inv_row_pass_fp<LOGN>(a0, twi, f, t0, as_fp(stage[0]));
+#pragma unroll
+        for (int e = 0; e < 8; e++) b0[row_strided_li<LOGN>(e)] = fp_bits(a0[e]);
+#pragma unroll
+        for (int e = 0; e < 8; e++) a1[e] = fp_reduce(a1[e], f);
+        inv_row_pass_fp<LOGN>(a1, twi, f, t0, as_fp(stage[1]));
+#pragma unroll
+        for (int e = 0; e < 8; e++) b1[row_strided_li<LOGN>(e)] = fp_bits(a1[e]);
+        return;
     }
     u64 r0[8], r1[8];
 #pragma unroll
@@ -553,6 +654,63 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_md_fwd_col(DView R, u64 *T2,
     fwd_col_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, smem);
 #pragma unroll
     for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
+}
+
+// (6+7) fused: inverse column pass of the divisor-prime limb (special prime P for a key switch, last data
+// prime for a rescale; its row pass is in R), the "+ half" of SEAL's rounding, and on the same tile the
+// column pass of (r' mod q_j) - (half mod q_j) for every remaining prime j.
+// grid: (COL_TILES, nsplit, instances); part p handles j = p, p + nsplit, ...
+template <int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_md_invcol_fwdcol(DView R, u64 *T2, int Lout, int a, int nsplit, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[2][NTT_TILE];
+    pdl_launch_dependents();
+    const int part = blockIdx.y, z = blockIdx.z;
+    const u64 *in = R.data + z * R.bs;
+    const ModConst ma = load_mod(t, a);
+    const FpConst fa = t.fp[a];
+    const u64 half = t.round_half ? (ma.p >> 1) : 0;
+    const int c0 = blockIdx.x * 32;
+    u64 v[8];
+    pdl_wait();
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = in[col_fine_idx<LOGN>(c0, e)];
+    if (fa.ok != 0.0) {
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = bits_fp(v[e]);
+        inv_col_pass_fp<LOGN>(xd, t.twid + (size_t)a * G::N, fa, as_fp(smem[0]));
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = csub(fp_to_canonical(xd[e], fa) + half, ma.p);
+    } else {
+        inv_col_pass<LOGN>(v, t.twi + (size_t)a * G::N, ma, smem[0]);
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = csub(csub(csub(v[e], ma.p2), ma.p) + half, ma.p);
+    }
+    int buf = 1;
+    for (int j = part; j < Lout; j += nsplit) {
+        const ModConst m = load_mod(t, j);
+        const FpConst f = t.fp[j];
+        const u64 hm = t.round_half ? t.halfmod[a * t.K + j] : 0;
+        const bool need_reduce = ma.p >= m.p4;   // else r' + q_j - hm < 8 q_j is already a valid lazy input
+        u64 *out = T2 + ((u64)z * Lout + j) * G::N;
+        u64 x[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = need_reduce ? submod(reduce64(v[e], m), hm, m.p) : v[e] + m.p - hm;
+        if (f.ok != 0.0) {   // x < 5 q_j: exact as doubles
+            double xd[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+            fwd_col_pass_fp<LOGN>(xd, t.twfd + (size_t)j * G::N, f, as_fp(smem[buf]));
+#pragma unroll
+            for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = fp_bits(xd[e]);
+        } else {
+            fwd_col_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, smem[buf]);
+#pragma unroll
+            for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
+        }
+        buf ^= 1;
+    }
 }
 
 // (8) mod-down / rescale, row pass with the epilogue
@@ -640,11 +798,21 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *T2, DV
 // Key-switch keys are static: at registration the engine makes a private copy in which, inside every 2048-word
 // tile, word pair v (0..3) of thread t (0..255) is stored at 512 v + 2 t instead of 8 t + 2 v, so that the
 // inner-product kernels' 16-byte key loads are contiguous across a warp.
-__global__ void k_retile_key(const u64 *src, u64 *dst) {
+__global__ void k_retile_key(const u64 *src, u64 *dst, int log_n, Tables t) {
     const size_t base = (size_t)blockIdx.x * NTT_TILE;
+    // limb of this tile: layout [digit][k][limb j < K][N]; small-prime limbs are stored as doubles so that the
+    // FP64 inner-product kernel needs no integer -> double conversion per key word (values < 2^41: exact)
+    const bool as_double = t.fp[(int)((base >> log_n) % (size_t)t.K)].ok != 0.0;
     const ulonglong2 *s = reinterpret_cast<const ulonglong2 *>(src + base + 8 * threadIdx.x);
 #pragma unroll
-    for (int v = 0; v < 4; v++) *reinterpret_cast<ulonglong2 *>(dst + base + 512 * v + 2 * threadIdx.x) = s[v];
+    for (int v = 0; v < 4; v++) {
+        ulonglong2 w = s[v];
+        if (as_double) {
+            w.x = fp_bits(fp_from_u64(w.x));
+            w.y = fp_bits(fp_from_u64(w.y));
+        }
+        *reinterpret_cast<ulonglong2 *>(dst + base + 512 * v + 2 * threadIdx.x) = w;
+    }
 }
 
 // =============================================================================== element-wise

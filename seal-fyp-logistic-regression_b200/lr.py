@@ -186,7 +186,7 @@ class ColumnLayout:
 
 
 def column_epoch_gradient(ev, cols, labels, w_bcast, C, B, scale, keys, encoder, encryptor, degree=7,
-                          method="tree", dot_method="reference"):
+                          method="tree", dot_method="reference", units=None):
     """One pass of the gradient loop over the mini-batches held by this GPU (column layout).
 
     cols    : batch M*C of column ciphertexts (entry m*C + j)
@@ -197,7 +197,12 @@ def column_epoch_gradient(ev, cols, labels, w_bcast, C, B, scale, keys, encoder,
     Per mini-batch the evaluator sequence is: z = sum_j multiply(col_j, w_j); relinearize; rescale;
     sigmoid polynomial (Tree_cipher / Horner_cipher); sub labels; then, per feature j, the reference's
     cipher_dot_product(col_j, pred - y, B) and the one-hot mask e_j (update_weights :295-311);
-    add_many; rescale."""
+    add_many; rescale.
+
+    `units` (optional) restricts the gradient dot products to a list of (mini-batch, feature) pairs -- the
+    sharding unit when ONE problem is split over several GPUs ("shard features j and
+    mini-batches"); the prediction is still evaluated for every mini-batch held here, the result is the
+    partial gradient sum over `units` (combine with parallel.combine_partials)."""
     M = labels.batch
     wb = Ciphertext(w_bcast.ctx, w_bcast.data.repeat(M, 1, 1, 1), w_bcast.limbs, w_bcast.scale)
     prods = ev.multiply(cols, wb)                                         # M*C size-3 products
@@ -213,12 +218,23 @@ def column_epoch_gradient(ev, cols, labels, w_bcast, C, B, scale, keys, encoder,
     pred.scale = lab.scale
     pred_labels = ev.sub(pred, lab)                                       # batch M
     colv = ev.mod_switch_to(cols, pred_labels.limbs)
-    pl = Ciphertext(cols.ctx, pred_labels.data.repeat_interleave(C, dim=0), pred_labels.limbs, pred_labels.scale)
-    grads = cipher_dot_product(ev, colv, pl, B, keys, method=dot_method)  # M*C chains in lock-step
     masks = np.zeros((C, C))
     masks[np.arange(C), np.arange(C)] = 1.0
-    mask_pt = encoder.encode(masks, scale, limbs=grads.limbs)
-    mp = Ciphertext(cols.ctx, mask_pt.data.repeat(M, 1, 1, 1), mask_pt.limbs, mask_pt.scale)
+    if units is None:
+        pl = Ciphertext(cols.ctx, pred_labels.data.repeat_interleave(C, dim=0), pred_labels.limbs, pred_labels.scale)
+        grads = cipher_dot_product(ev, colv, pl, B, keys, method=dot_method)  # M*C chains in lock-step
+        mask_pt = encoder.encode(masks, scale, limbs=grads.limbs)
+        mp = Ciphertext(cols.ctx, mask_pt.data.repeat(M, 1, 1, 1), mask_pt.limbs, mask_pt.scale)
+    else:
+        dev = cols.data.device
+        ci = torch.tensor([m * C + j for m, j in units], device=dev)
+        mi = torch.tensor([m for m, _ in units], device=dev)
+        ji = torch.tensor([j for _, j in units], device=dev)
+        csel = Ciphertext(cols.ctx, colv.data.index_select(0, ci), colv.limbs, colv.scale)
+        pl = Ciphertext(cols.ctx, pred_labels.data.index_select(0, mi), pred_labels.limbs, pred_labels.scale)
+        grads = cipher_dot_product(ev, csel, pl, B, keys, method=dot_method)  # len(units) chains in lock-step
+        mask_pt = encoder.encode(masks, scale, limbs=grads.limbs)
+        mp = Ciphertext(cols.ctx, mask_pt.data.index_select(0, ji), mask_pt.limbs, mask_pt.scale)
     ev.multiply_plain_inplace(grads, mp)
     gradient = ev.add_many(grads)                                         # over features and mini-batches
     ev.rescale_to_next_inplace(gradient)

@@ -23,6 +23,36 @@ def shard_units(n_units, rank, world_size):
     return list(range(rank, n_units, world_size))
 
 
+def naf_weight(steps):
+    """number of key switches SEAL's rotate_vector spends on `steps` with the default power-of-two Galois
+    keys: the number of non-zero digits of its non-adjacent form (util::naf; SURVEY.md A.6)"""
+    v, w = abs(int(steps)), 0
+    while v:
+        if v & 1:
+            z = 2 - (v & 3)
+            v -= z
+            w += 1
+        v >>= 1
+    return w
+
+
+def shard_units_weighted(weights, rank, world_size):
+    """partition units by COST instead of index: longest-processing-time greedy (heaviest unit first, always
+    onto the least-loaded rank; ties broken by rank index so every rank computes the same assignment).
+    For the diagonals of a linear transform the cost of diagonal l is naf_weight(l) key switches: `l mod G`
+    gives rank 0 all even diagonals (157 key switches at d = 128, G = 2) and rank 1 all odd ones (199);
+    this split is 178 / 178.  Returns this rank's unit indices in increasing order."""
+    order = sorted(range(len(weights)), key=lambda u: (-weights[u], u))
+    load = [0] * world_size
+    mine = []
+    for u in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        load[r] += weights[u]
+        if r == rank:
+            mine.append(u)
+    return sorted(mine)
+
+
 def gather_partials(t):
     """all-gather one tensor per rank -> [G, ...] on every rank (any backend)"""
     rank, G = world()
