@@ -100,11 +100,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("CKKS_B200_LIB", LIB_PATH)   # profiling aid: A/B an experimental build (profiles/build_variant.sh)
+    if not os.path.exists(path):
         raise ImportError(
             "libckks_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU or PyTorch fallback for the CKKS engine)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError if the symbol is missing
         fn.restype = res

@@ -54,8 +54,10 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    static const bool no_pdl = getenv("CKKS_NO_PDL") != nullptr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
+    // programmatic dependent launch paid off for the 9-launch pipeline of round 1; with the fused 5/6-launch pipeline it is
+    // neutral at large batches and costs 20 % at small ones (profiles/r02_keyswitch_experiments.md): off unless CKKS_PDL=1
+    static const bool use_pdl = getenv("CKKS_PDL") != nullptr && atoi(getenv("CKKS_PDL")) != 0;
+    cfg.numAttrs = use_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -184,6 +186,7 @@ extern "C" int ckks_ctx_create(int log_n, int n_primes, const uint64_t *primes, 
     if (const char *e = getenv("CKKS_FUSE")) c->fuse = atoi(e);
     if (const char *e = getenv("CKKS_SPLIT1")) c->split1 = atoi(e);
     if (const char *e = getenv("CKKS_SPLIT3")) c->split3 = atoi(e);
+    if (const char *e = getenv("CKKS_WS_CAP_MB")) c->ws_cap = (size_t)atol(e) << 20;
     if (const char *e = getenv("CKKS_LANES")) c->chain_lanes = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
     *out = c;
     return CKKS_OK;
@@ -539,7 +542,8 @@ static int get_perm(ckks_ctx *c, uint64_t g, const uint32_t **out) {
 // nsplit of the fused column kernels: one CTA per tile does every target prime when the launch already fills the
 // GPU (148 SMs x 4 resident CTAs); a small batch splits the targets over up to `maxsplit` CTAs per tile instead
 static int pick_split(int forced, int tiles, int maxsplit) {
-    int ns = forced > 0 ? forced : (tiles >= 592 ? 1 : (592 + tiles - 1) / tiles);
+    (void)tiles;   // measured (profiles/r02_keyswitch_experiments.md): splitting never wins, not even at batch 4
+    int ns = forced > 0 ? forced : 1;
     if (ns > maxsplit) ns = maxsplit;
     return ns < 1 ? 1 : ns;
 }

@@ -515,8 +515,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
 
 // FP64 variant for output limbs with a small prime: transform, products and the running sums all
 // stay on the FP64 pipe (|sum| < 2p per term, at most 32 terms: exact), one canonicalisation at the end
+#ifndef V_MACFP_OCC
+#define V_MACFP_OCC 3
+#endif
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, int fuse_inv, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, V_MACFP_OCC) k_ks_mac_fp(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, int fuse_inv, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ __align__(128) u64 stage[2][NTT_TILE];   // TMA-staged tiles; the current one is also the exchange buffer
     __shared__ u64 bars[2];
@@ -547,8 +550,23 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsR
     if (threadIdx.x == 0 && nxt < L) tma_load_tile(stage[0], tile_of(nxt), NTT_TILE * 8, &bars[0]);
     for (int i = 0; i < L; i++) {
         double x[8];
+#ifdef V_MACFP_EARLYKEY
+        // the digit's key words are requested before its transform: ~300 cycles of L2 latency hidden behind the row pass
+        ulonglong2 ka[4], kc[4];
+        {
+            const int koff = rt.key_tiled ? 2 * threadIdx.x : 8 * threadIdx.x, kstep = rt.key_tiled ? 256 : 1;
+            const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + koff);
+            const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + koff);
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                ka[v] = __ldg(k0 + kstep * v);
+                kc[v] = __ldg(k1 + kstep * v);
+            }
+        }
+#else
         prefetch_l2(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
         prefetch_l2(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
+#endif
         if (i == pj) {
             const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
             u64 xi[8];
@@ -575,6 +593,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsR
             fwd_row_pass_fp<LOGN>(x, tw, f, t0, as_fp(stage[slot]));   // lazy, |x| < 32p
             slot ^= 1;
         }
+#ifdef V_MACFP_EARLYKEY
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            ulonglong2 a = ka[v], c = kc[v];
+#else
         // standard layout: the thread's 8 words are contiguous (4 x 16 B, 64 B apart between threads: every warp
         // load touches 16 lines); tiled layout: word pair v of thread t sits at 512 v + 2 t (4 lines per warp load)
         const int koff = rt.key_tiled ? 2 * threadIdx.x : 8 * threadIdx.x, kstep = rt.key_tiled ? 256 : 1;
@@ -583,6 +606,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_fp(const u64 *T1, KsR
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             ulonglong2 a = __ldg(k0 + kstep * v), c = __ldg(k1 + kstep * v);
+#endif
             // engine-owned (tiled) key copies hold small-prime limbs as doubles already (k_retile_key)
             const double kax = rt.key_tiled ? bits_fp(a.x) : fp_from_u64(a.x), kay = rt.key_tiled ? bits_fp(a.y) : fp_from_u64(a.y);
             const double kcx = rt.key_tiled ? bits_fp(c.x) : fp_from_u64(c.x), kcy = rt.key_tiled ? bits_fp(c.y) : fp_from_u64(c.y);
@@ -718,8 +742,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_invcol_fwdcol(DView R, u6
 // MODE 0 (rescale): no base.  MODE 1 (relinearize): base = in[b][k].  MODE 2 (Galois):
 // base = permuted in[b][0] for k == 0 and nothing for k == 1 (SEAL wipes c1 before switching).
 // z = b*S + s enumerates (ciphertext, poly).
+#ifndef V_MDROW_OCC
+#define V_MDROW_OCC 4
+#endif
 template <int LOGN, int MODE>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *T2, DView minuend, KsRoute rt, int S, int Lout, int a, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, V_MDROW_OCC) k_md_fwd_row(const u64 *T2, DView minuend, KsRoute rt, int S, int Lout, int a, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     pdl_launch_dependents();
@@ -736,6 +763,12 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *T2, DV
     pdl_wait();
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
+    const u64 *mi = minuend.data + b * minuend.bs + s * minuend.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
+    u64 *out = dst.data + sl.entry * dst.bs + s * dst.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
+    u64 mv[8], bv[8];
+#ifdef V_MDROW_EARLY
+    load8(mv, mi);   // the accumulator limb is requested before the transform instead of after it
+#endif
     double xd[8];
     const bool fp = f.ok != 0.0;
     if (fp) {
@@ -745,12 +778,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_fwd_row(const u64 *T2, DV
     } else {
         fwd_row_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, t0, smem);
     }
-    const u64 *mi = minuend.data + b * minuend.bs + s * minuend.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
-    u64 *out = dst.data + sl.entry * dst.bs + s * dst.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
     // all epilogue loads are issued before the first store (out may alias base, so the compiler
     // would otherwise serialise load -> store -> load ...)
-    u64 mv[8], bv[8];
+#ifndef V_MDROW_EARLY
     load8(mv, mi);
+#endif
     if (MODE == 1) {
         load8(bv, base.data + sl.entry * base.bs + s * base.ps + (u64)j * G::N + t0 + 8 * threadIdx.x);
     } else if (MODE == 2) {
