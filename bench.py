@@ -347,9 +347,11 @@ def run_gpu(args):
             self.h2d_bytes = sum(t.numel() * 8 for t in self.host.values())
 
         def epoch(self, cols, labs, wb, wct, k=None, dot_method="reference"):
+            # all-gather of the partial gradient ciphertexts + mod-q add kernel, before the final rescale (bit-identical
+            # to the unsharded epoch)
             grad = lr.column_epoch_gradient(ev, cols, labs, wb, C_FEAT, B_MINI, SCALE, k or keys, enc, encr,
-                                            degree=DEGREE, method="tree", dot_method=dot_method, units=self.units)
-            grad = par.combine_partials(ev, grad)     # all-gather of the partial ciphertexts + mod-q add kernel
+                                            degree=DEGREE, method="tree", dot_method=dot_method, units=self.units,
+                                            combine=lambda g: par.combine_partials(ev, g))
             return grad, lr.apply_gradient(ev, grad, wct, LR, self.R_total, SCALE, enc)
 
         def resident(self):

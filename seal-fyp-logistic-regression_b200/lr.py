@@ -186,7 +186,7 @@ class ColumnLayout:
 
 
 def column_epoch_gradient(ev, cols, labels, w_bcast, C, B, scale, keys, encoder, encryptor, degree=7,
-                          method="tree", dot_method="reference", units=None):
+                          method="tree", dot_method="reference", units=None, combine=None):
     """One pass of the gradient loop over the mini-batches held by this GPU (column layout).
 
     cols    : batch M*C of column ciphertexts (entry m*C + j)
@@ -202,7 +202,9 @@ def column_epoch_gradient(ev, cols, labels, w_bcast, C, B, scale, keys, encoder,
     `units` (optional) restricts the gradient dot products to a list of (mini-batch, feature) pairs -- the
     sharding unit when ONE problem is split over several GPUs ("shard features j and
     mini-batches"); the prediction is still evaluated for every mini-batch held here, the result is the
-    partial gradient sum over `units` (combine with parallel.combine_partials)."""
+    partial gradient sum over `units`.  `combine` (optional) is applied to the partial sum BEFORE the final rescale --
+    pass parallel.combine_partials there (all-gather + mod-q add): summing first and rescaling once keeps the
+    sharded result bit-identical to the unsharded one (rescale rounds, so it does not commute with the sum)."""
     M = labels.batch
     wb = Ciphertext(w_bcast.ctx, w_bcast.data.repeat(M, 1, 1, 1), w_bcast.limbs, w_bcast.scale)
     prods = ev.multiply(cols, wb)                                         # M*C size-3 products
@@ -237,6 +239,8 @@ def column_epoch_gradient(ev, cols, labels, w_bcast, C, B, scale, keys, encoder,
         mp = Ciphertext(cols.ctx, mask_pt.data.index_select(0, ji), mask_pt.limbs, mask_pt.scale)
     ev.multiply_plain_inplace(grads, mp)
     gradient = ev.add_many(grads)                                         # over features and mini-batches
+    if combine is not None:
+        gradient = combine(gradient)                                      # ... and over GPUs
     ev.rescale_to_next_inplace(gradient)
     return force_scale_pow2(gradient)
 

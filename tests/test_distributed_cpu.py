@@ -73,3 +73,36 @@ def test_shard_units_partition():
             parts = [par.shard_units(n, r, G) for r in range(G)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_weighted_shards_balance_naf_cost():
+    """Linear_Transform diagonals are split by key-switch cost (NAF weight), not by index"""
+    par = importlib.import_module(PKG + ".parallel")
+    from oracle import pyoracle as po
+    for l in list(range(-130, 130)) + [4095, -8192]:
+        assert par.naf_weight(l) == len(po.naf(l)), l
+    for d in (64, 128):
+        w = [par.naf_weight(l) for l in range(d)]
+        for G in (1, 2, 4, 8):
+            parts = [par.shard_units_weighted(w, r, G) for r in range(G)]
+            assert sorted(sum(parts, [])) == list(range(d))                     # a partition
+            loads = [sum(w[u] for u in p) for p in parts]
+            assert max(loads) - min(loads) <= 1, (d, G, loads)                  # l mod G: 156 vs 199 at d=128, G=2
+            assert all(p == sorted(p) for p in parts)
+
+
+def test_strong_scaling_units_partition_the_problem():
+    """bench.py --scaling strong: the 32 (mini-batch, feature) gradient chains of one 8 x 32768 problem"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    M, C = bench.R_PER_GPU // bench.B_MINI, bench.C_FEAT
+    for G in (1, 2, 4, 8, 16, 32):
+        parts = [bench.strong_units(r, G) for r in range(G)]
+        assert sorted(sum(parts, [])) == [(m, j) for m in range(M) for j in range(C)]
+        assert len({len(p) for p in parts}) == 1
+        if G <= M:
+            assert all(len({m for m, _ in p}) == M // G for p in parts)        # whole mini-batches per GPU
+    with pytest.raises(SystemExit):
+        bench.strong_units(0, 3)

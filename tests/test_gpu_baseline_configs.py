@@ -289,3 +289,60 @@ def test_config1_pulsar_real_data_update_weights(eng):
     assert np.abs(got - ref_step).max() < 0.05
     assert abs(pulsar.cost_function(Xs.astype(np.float32), y, got) - gold["cost_after_iteration_0"]) < 0.02
     assert abs(pulsar.cost_function(Xs.astype(np.float32), y, got) - pulsar.cost_function(Xs.astype(np.float32), y, want_poly)) < 1e-5
+
+
+def test_gradient_unit_sharding_is_bit_identical(make_fixture):
+    """strong scaling of config 5 (bench.py --scaling strong): the (mini-batch, feature) gradient units of ONE problem are
+    split over ranks; the mod-q sum of the ranks' partial gradient ciphertexts (what all-gather + ckks_add_many
+    computes) must equal the unsharded gradient ciphertext bit for bit -- including the 8-GPU split where the features
+    of one mini-batch are divided between two ranks"""
+    wl, lr, client = _mods()
+    fx = make_fixture(12, [50] + [40] * 8 + [50], steps=tuple(s for i in range(11) for s in (1 << i, -(1 << i))))
+    br = Bridge(fx)
+    rng = np.random.default_rng(77)
+    scale = 2.0 ** 40
+    C, B, M, degree = 4, 8, 2, 7
+    R = B * M
+    slots = fx.n // 2
+    X = rng.normal(0, 1, (R, C))
+    y = (rng.uniform(0, 1, R) > 0.5).astype(float)
+    w0 = rng.uniform(-1, 1, C)
+    lay = lr.ColumnLayout(R, C, B, slots)
+    cols = fx.ctx.upload(np.stack([_enc(fx, 900 + i, v, scale) for i, v in enumerate(lay.columns(X))]), scale=scale)
+    labs = fx.ctx.upload(np.stack([_enc(fx, 950 + i, v, scale) for i, v in enumerate(lay.labels(y))]), scale=scale)
+    wb = fx.ctx.upload(np.stack([_enc(fx, 980 + j, np.full(slots, w0[j]), scale) for j in range(C)]), scale=scale)
+
+    def grad(units=None, sub=None, combine=None):
+        br.seed = 8000
+        c, l = cols, labs
+        if sub is not None:          # a rank holds only the mini-batches it touches
+            idx = [m * C + j for m in sub for j in range(C)]
+            c = fx.eng.Ciphertext(fx.ctx, cols.data[idx].contiguous(), cols.limbs, cols.scale)
+            l = fx.eng.Ciphertext(fx.ctx, labs.data[list(sub)].contiguous(), labs.limbs, labs.scale)
+        return lr.column_epoch_gradient(fx.ev, c, l, wb, C, B, scale, fx.keys, br, br, degree=degree, method="tree", units=units,
+                                        combine=combine)
+
+    full = grad()
+    # three "ranks": features 0-1 and 2-3 of mini-batch 0, all of mini-batch 1.  Pass 1 records every rank's partial sum
+    # (what it would contribute to the all-gather); pass 2 runs one rank with combine = sum of all partials mod q.
+    partials = []
+
+    def record(g):
+        partials.append(g.clone())
+        return g
+
+    shards = [dict(units=[(0, 0), (0, 1)], sub=[0]), dict(units=[(0, 2), (0, 3)], sub=[0]), dict(units=None, sub=[1])]
+    for sh in shards:
+        grad(combine=record, **sh)
+
+    def gathered_sum(g):
+        total = partials[0]
+        for p in partials[1:]:
+            total = fx.ev.add(total, p)
+        return total
+
+    combined = grad(combine=gathered_sum, **shards[0])
+    assert combined.limbs == full.limbs and combined.scale == full.scale
+    assert np.array_equal(combined.numpy(), full.numpy())
+    dec = fx.orc.decode(fx.orc.decrypt(fx.sk, combined.numpy()[0]), combined.scale)[:C]
+    assert np.abs(dec - X.T @ (lr.sigmoid_approx(X @ w0, degree) - y)).max() < 1e-2
