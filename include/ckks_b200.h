@@ -78,8 +78,12 @@ uint64_t ckks_ctx_launch_count(const ckks_ctx *ctx);
 void ckks_ctx_reset_launch_count(ckks_ctx *ctx);
 
 /* ---- memory / stream helpers for hosts that do not bring their own allocator.  Device buffers come
- * from the stream-ordered memory pool of the device (cudaMallocAsync / cudaFreeAsync on the default
- * stream, freed memory kept for reuse). */
+ * from the stream-ordered memory pool of the device (cudaMallocAsync / cudaFreeAsync, freed memory kept
+ * for reuse).  The _async forms are ordered on the caller's stream `s`: use them (with the stream the buffer is
+ * computed on) when that stream is a non-blocking one; the plain forms are the same calls on the default stream
+ * (what the seal/seal.h shim does -- it issues every call on the default stream). */
+int ckks_dev_alloc_async(ckks_ctx *ctx, size_t bytes, void **out, ckks_stream s);
+int ckks_dev_free_async(ckks_ctx *ctx, void *p, ckks_stream s);
 int ckks_dev_alloc(ckks_ctx *ctx, size_t bytes, void **out);
 int ckks_dev_free(ckks_ctx *ctx, void *p);
 int ckks_host_alloc(size_t bytes, void **out);   /* pinned */
@@ -137,7 +141,11 @@ uint64_t ckks_galois_elt_from_step(const ckks_ctx *ctx, int steps);
 /* key registry = SEAL RelinKeys + GaloisKeys.  Registering a key captures its contents: the engine keeps a private
  * copy in the tile layout its inner-product kernels read fastest, and every entry point that is later given the
  * same pointer (ckks_relinearize, ckks_apply_galois, the keyset-based calls) uses that copy.  The caller's buffer
- * must stay allocated and unchanged while a keyset references it; register it again after changing it. */
+ * must stay allocated and unchanged while a keyset references it; register it again after changing it.
+ * ckks_keyset_set_relin / _set_galois are set-up calls and SYNCHRONOUS with respect to every stream of the device (the
+ * device is drained before the key is captured and the capture is complete on return): the key may have been produced on
+ * any stream and may be used on any stream afterwards.  Rotation plans compiled before a key was replaced pick up the
+ * new copy at their next ckks_rotate_plan. */
 int ckks_keyset_create(ckks_ctx *ctx, ckks_keyset **out);
 void ckks_keyset_destroy(ckks_keyset *ks);
 int ckks_keyset_set_relin(ckks_keyset *ks, const uint64_t *rlk);
@@ -211,10 +219,16 @@ int ckks_decode(ckks_ctx *ctx, const ckks_view *in, double scale, double *values
  * linear_transformation2.cpp:236-239) and Encryptor::encrypt (:347-349).  `out` is a size-1 view of
  * out->batch polynomials over limbs [0, out->limbs); ternary and normal polynomials hold the same small
  * integer in every limb and are returned in NTT form, uniform polynomials are independent per limb.
- * Counter-based generator keyed by `seed`; (`seed`, `stream_id`) must not repeat between calls. */
+ * The generator is ChaCha20 (RFC 8439 block function) in counter mode under a 256-bit key: a CSPRNG like SEAL 3.4.5's
+ * own (Blake2-based) default generator.  (`key`, `stream_id`) must not repeat between calls.
+ *   ckks_sample_keyed  -- `key` = 32 bytes from a cryptographic source (the seal/seal.h shim and client.py read the
+ *                         operating system's CSPRNG): the entry point for real keys and encryptions.
+ *   ckks_sample        -- reproducible variant for tests and benchmarks: the 64-bit `seed` is expanded into the key, so
+ *                         the stream has at most 64 bits of entropy.  NOT for real keys. */
 #define CKKS_SAMPLE_TERNARY 0
 #define CKKS_SAMPLE_NORMAL 1
 #define CKKS_SAMPLE_UNIFORM 2
+int ckks_sample_keyed(ckks_ctx *ctx, int kind, const uint8_t key[32], uint64_t stream_id, const ckks_view *out, ckks_stream s);
 int ckks_sample(ckks_ctx *ctx, int kind, uint64_t seed, uint64_t stream_id, const ckks_view *out, ckks_stream s);
 
 #ifdef __cplusplus

@@ -50,6 +50,8 @@ SIGNATURES = {
     "ckks_ctx_reset_launch_count": (None, [C.c_void_p]),
     "ckks_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, _vpp]),
     "ckks_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ckks_dev_alloc_async": (C.c_int, [C.c_void_p, C.c_size_t, _vpp, C.c_void_p]),
+    "ckks_dev_free_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ckks_host_alloc": (C.c_int, [C.c_size_t, _vpp]),
     "ckks_host_free": (C.c_int, [C.c_void_p]),
     "ckks_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -90,6 +92,7 @@ SIGNATURES = {
     "ckks_encode_scalar": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _VP, C.c_void_p]),
     "ckks_decode": (C.c_int, [C.c_void_p, _VP, C.c_double, C.c_void_p, C.c_void_p]),
     "ckks_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, _VP, C.c_void_p]),
+    "ckks_sample_keyed": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, _VP, C.c_void_p]),
 }
 
 _lib = None

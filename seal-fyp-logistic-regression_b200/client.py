@@ -6,6 +6,8 @@ GPU through the C ABI (NTT, dyadic products, divide-by-last-prime); the host onl
 randomness (numpy) and does the floating-point embedding / CRT composition.  Results are
 compared with tolerance, never bit-exactly (SEAL's own randomness is unpinned).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -133,14 +135,18 @@ class CKKSEncoder:
 class _RingOps:
     """device ring helpers shared by key generation / encryption / decryption"""
 
-    def __init__(self, ctx, rng):
-        self.ctx, self.rng = ctx, rng
+    def __init__(self, ctx, seed=None):
+        """seed=None (the default): a fresh 256-bit ChaCha20 key from the operating system's CSPRNG (os.urandom) --
+        what real keys and encryptions must use.  An integer seed gives a reproducible stream for tests and
+        benchmarks (at most 64 bits of entropy: never for real keys)."""
+        self.ctx = ctx
         self.ev = Evaluator(ctx)
-        self._seed = int(rng.integers(0, 2 ** 63))
+        self._seed = os.urandom(32) if seed is None else int(seed) & (2 ** 64 - 1)
         self._stream = 0
 
     def _draw(self, kind, count, limbs):
-        """sampling runs on the device (ckks_sample): counter-based generator keyed by this object's seed"""
+        """sampling runs on the device (ckks_sample_keyed / ckks_sample): ChaCha20 in counter mode keyed by this
+        object's key, one stream id (nonce) per call"""
         self._stream += 1
         return self.ev.sample(kind, self._seed, self._stream, count, limbs)
 
@@ -177,9 +183,10 @@ class KeyGenerator:
     """SEAL KeyGenerator: ternary secret, public key, relinearisation and Galois keys
     (SURVEY.md A.5), at the key level (all K primes)."""
 
-    def __init__(self, ctx, seed=0):
+    def __init__(self, ctx, seed=None):
+        """seed=None draws the generator key from os.urandom; an int makes the keys reproducible (tests, bench)"""
         self.ctx = ctx
-        self.ops = _RingOps(ctx, np.random.default_rng(seed))
+        self.ops = _RingOps(ctx, seed)
         self._sk = self.ops.ternary_ntt(1, ctx.K)[0]      # [K][N]
 
     def secret_key(self):
@@ -234,9 +241,9 @@ class Encryptor:
     """SEAL Encryptor (public key): (u pk + e) one level above the target, divide-and-round by
     the extra prime (the rescale kernels), plaintext added to c0."""
 
-    def __init__(self, ctx, public_key, seed=1):
+    def __init__(self, ctx, public_key, seed=None):
         self.ctx, self.pk = ctx, public_key
-        self.ops = _RingOps(ctx, np.random.default_rng(seed))
+        self.ops = _RingOps(ctx, seed)   # None: encryption randomness keyed from os.urandom
 
     def encrypt(self, pt):
         ctx, ops, ev = self.ctx, self.ops, self.ops.ev
@@ -260,7 +267,7 @@ class Decryptor:
 
     def __init__(self, ctx, secret_key):
         self.ctx, self.sk = ctx, secret_key
-        self.ops = _RingOps(ctx, np.random.default_rng(0))
+        self.ops = _RingOps(ctx, 0)      # the decryptor draws nothing
 
     def decrypt(self, ct):
         ops, ev, L = self.ops, self.ops.ev, ct.limbs

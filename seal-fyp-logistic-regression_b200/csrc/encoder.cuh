@@ -188,32 +188,40 @@ __global__ void k_dec_gather(const double2 *v, const uint32_t *kidx, double *val
 
 // ------------------------------------------------------------------------------------ sampling
 // KeyGenerator / Encryptor randomness on the device: SEAL's sample_poly_ternary, sample_poly_normal
-// (sigma 3.2, clipped at 6 sigma) and sample_poly_uniform.  Philox4x32-10 keyed by the caller's seed,
-// counter = (coefficient, polynomial, stream id): reproducible and order-independent.  Philox is a
-// statistical generator, not a CSPRNG -- the same holds for the std::mt19937_64 it replaces; a
-// deployment swaps in AES-CTR here.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+// (sigma 3.2, clipped at 6 sigma) and sample_poly_uniform.  The generator is ChaCha20 (RFC 8439 block
+// function, 20 rounds) under a 256-bit key supplied by the caller -- the seal/seal.h shim and client.py draw
+// that key from the operating system's CSPRNG -- with the block counter = (coefficient, polynomial | limb |
+// attempt) and the nonce = the caller's stream id: a cryptographic PRF in counter mode, reproducible and
+// order-independent.  (SEAL 3.4.5's default generator is likewise a CSPRNG: Blake2-based.)
+struct SampleKey {
+    uint32_t k[8];
+};
+__device__ __forceinline__ uint32_t rotl32(uint32_t v, int n) { return __funnelshift_l(v, v, n); }
+#define CHACHA_QR(a, b, c, d) \
+    a += b; d ^= a; d = rotl32(d, 16); c += d; b ^= c; b = rotl32(b, 12); a += b; d ^= a; d = rotl32(d, 8); c += d; b ^= c; b = rotl32(b, 7);
+// first four output words of the ChaCha20 block (key, counter = {c0, c1}, nonce = {n0, n1})
+__device__ __forceinline__ uint4 chacha20_block4(const SampleKey &key, uint32_t c0, uint32_t c1, uint32_t n0, uint32_t n1) {
+    uint32_t x0 = 0x61707865u, x1 = 0x3320646eu, x2 = 0x79622d32u, x3 = 0x6b206574u;
+    uint32_t x4 = key.k[0], x5 = key.k[1], x6 = key.k[2], x7 = key.k[3], x8 = key.k[4], x9 = key.k[5], x10 = key.k[6], x11 = key.k[7];
+    uint32_t x12 = c0, x13 = c1, x14 = n0, x15 = n1;
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
+        CHACHA_QR(x0, x4, x8, x12) CHACHA_QR(x1, x5, x9, x13) CHACHA_QR(x2, x6, x10, x14) CHACHA_QR(x3, x7, x11, x15)
+        CHACHA_QR(x0, x5, x10, x15) CHACHA_QR(x1, x6, x11, x12) CHACHA_QR(x2, x7, x8, x13) CHACHA_QR(x3, x4, x9, x14)
     }
-    return c;
+    return make_uint4(x0 + 0x61707865u, x1 + 0x3320646eu, x2 + 0x79622d32u, x3 + 0x6b206574u);
 }
 
 // kind 0: ternary {-1,0,1}; kind 1: rounded normal, sigma 3.2, |v| <= 19.  The same small integer is
 // reduced into every limb (coefficient form; the caller transforms).
-__global__ void k_sample_small(DView out, int limbs, int n, int kind, u64 seed, u64 stream_id, Tables t) {
+__global__ void k_sample_small(DView out, int limbs, int n, int kind, SampleKey key, u64 stream_id, Tables t) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (j >= n) return;
-    const uint4 r = philox4x32_10(make_uint4((unsigned)j, (unsigned)b, (unsigned)stream_id, (unsigned)(stream_id >> 32)),
-                                  make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const uint4 r = chacha20_block4(key, (unsigned)j, (unsigned)b, (unsigned)stream_id, (unsigned)(stream_id >> 32));
     int v;
     if (kind == 0) {
-        v = (int)(((u64)r.x * 3) >> 32) - 1;
+        // uniform on {-1, 0, 1}: multiply-shift of a 64-bit draw (bias < 2^-62)
+        v = (int)__umul64hi(((u64)r.x << 32) | r.y, 3) - 1;
     } else {
         const double u1 = ((double)(((u64)r.x << 32) | r.y) + 0.5) * 5.421010862427522e-20;   // (0, 1]
         const double u2 = ((double)r.z + 0.5) * 2.3283064365386963e-10;
@@ -232,7 +240,7 @@ __global__ void k_sample_small(DView out, int limbs, int n, int kind, u64 seed, 
 // uniform residues in [0, q_l) for every limb by Lemire's multiply-shift with rejection: x uniform on
 // 64 bits, result hi64(x * q); draws whose low product word falls below 2^64 mod q are redrawn, which
 // makes the result exactly uniform (rejection probability q / 2^64 < 1/16 per draw).
-__global__ void k_sample_uniform(DView out, int limbs, int n, u64 seed, u64 stream_id, Tables t) {
+__global__ void k_sample_uniform(DView out, int limbs, int n, SampleKey key, u64 stream_id, Tables t) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (j >= n) return;
     u64 *o = out.data + (size_t)b * out.bs + j;
@@ -241,9 +249,9 @@ __global__ void k_sample_uniform(DView out, int limbs, int n, u64 seed, u64 stre
         const u64 thresh = (0 - p) % p;       // 2^64 mod p
         u64 res = 0;
         for (unsigned attempt = 0; attempt < 8; attempt++) {
-            const uint4 r = philox4x32_10(make_uint4((unsigned)j, (unsigned)b | ((unsigned)l << 20) | (attempt << 26),
-                                                     (unsigned)stream_id, (unsigned)(stream_id >> 32)),
-                                          make_uint2((unsigned)seed, ~(unsigned)(seed >> 32)));
+            // counter word 1: polynomial (20 bits) | limb (6 bits) | attempt (3 bits) | domain bit for "uniform"
+            const uint4 r = chacha20_block4(key, (unsigned)j, (unsigned)b | ((unsigned)l << 20) | (attempt << 26) | 0x80000000u,
+                                            (unsigned)stream_id, (unsigned)(stream_id >> 32));
             const u64 x = ((u64)r.x << 32) | r.y;
             res = __umul64hi(x, p);
             if (x * p >= thresh) break;        // unbiased draw (rejects with probability p / 2^64 < 1/16)

@@ -121,7 +121,7 @@ struct ckks_keyset {
 // the r-th NAF term of every entry that still has one, all in a single batched key switch.
 struct ckks_rotplan {
     ckks_ctx *ctx;
-    const ckks_keyset *ks;
+    ckks_keyset *ks;
     int batch = 0;
     std::vector<int> round_off, round_cnt;
     std::vector<int> zero_entries;
@@ -299,7 +299,7 @@ extern "C" int ckks_ctx_reserve(ckks_ctx *c, int batch, int limbs) {
 // Plaintext / Ciphertext): served from the device's stream-ordered memory pool on the default
 // stream, with the pool told to keep freed memory -- a plain cudaMalloc costs ~2 ms on this part
 // and cudaFree synchronises the device, which dominated the reference's programs.
-extern "C" int ckks_dev_alloc(ckks_ctx *c, size_t bytes, void **out) {
+extern "C" int ckks_dev_alloc_async(ckks_ctx *c, size_t bytes, void **out, ckks_stream s) {
     CU(cudaSetDevice(c->device));
     if (!c->pool_ready) {
         cudaMemPool_t pool;
@@ -308,17 +308,20 @@ extern "C" int ckks_dev_alloc(ckks_ctx *c, size_t bytes, void **out) {
         CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         c->pool_ready = true;
     }
-    if (cudaMallocAsync(out, bytes, (cudaStream_t)0) != cudaSuccess) {
+    if (cudaMallocAsync(out, bytes, (cudaStream_t)s) != cudaSuccess) {
         cudaGetLastError();
         return fail(CKKS_ERR_NOMEM, "device allocation failed");
     }
     return CKKS_OK;
 }
-extern "C" int ckks_dev_free(ckks_ctx *c, void *p) {
+extern "C" int ckks_dev_free_async(ckks_ctx *c, void *p, ckks_stream s) {
     CU(cudaSetDevice(c->device));
-    CU(cudaFreeAsync(p, (cudaStream_t)0));
+    CU(cudaFreeAsync(p, (cudaStream_t)s));
     return CKKS_OK;
 }
+// default-stream forms (what the seal/seal.h shim uses: it runs every call on the default stream)
+extern "C" int ckks_dev_alloc(ckks_ctx *c, size_t bytes, void **out) { return ckks_dev_alloc_async(c, bytes, out, nullptr); }
+extern "C" int ckks_dev_free(ckks_ctx *c, void *p) { return ckks_dev_free_async(c, p, nullptr); }
 extern "C" int ckks_host_alloc(size_t bytes, void **out) {
     if (cudaMallocHost(out, bytes) != cudaSuccess) return fail(CKKS_ERR_NOMEM, "pinned allocation failed");
     return CKKS_OK;
@@ -737,8 +740,13 @@ static int register_key(ckks_ctx *c, const uint64_t *key) {
         return fail(CKKS_ERR_NOMEM, "device allocation failed");
     }
     t.refs++;
+    // Registration is a set-up step, not a hot-path call, and it is SYNCHRONOUS with respect to every stream: the caller's
+    // key buffer may have been produced on any (non-blocking) stream and the first key switch may run on any other, so
+    // the device is drained before the capture and the capture is complete on return.
+    CU(cudaDeviceSynchronize());
     k_retile_key<<<(unsigned)(words / NTT_TILE), NTT_THREADS>>>((const u64 *)key, t.copy, c->log_n, c->t);   // (re)capture the contents
     LAUNCH_CHECK(c);
+    CU(cudaDeviceSynchronize());
     return CKKS_OK;
 }
 static void unregister_key(ckks_ctx *c, const uint64_t *key) {
@@ -1058,6 +1066,9 @@ extern "C" int ckks_rotate_plan(ckks_ctx *c, const ckks_rotplan *p, const ckks_v
         if (scratch->data == in->data || scratch->data == out->data) return fail(CKKS_ERR_INVALID, "scratch must be distinct storage");
     }
     CU(cudaSetDevice(c->device));
+    // a Galois key replaced after the plan was compiled has a new engine-owned copy: refresh the device-side key table
+    // (no-op unless the keyset changed) and make sure every key the plan selects is still registered
+    if ((rc = sync_key_tables(p->ks))) return rc;
     cudaStream_t st = (cudaStream_t)s;
     KsRoute rt{};
     rt.v[0] = dv(in);
@@ -1319,7 +1330,7 @@ extern "C" int ckks_decode(ckks_ctx *c, const ckks_view *in, double scale, doubl
 }
 
 // ------------------------------------------------------------------------------------ sampling
-extern "C" int ckks_sample(ckks_ctx *c, int kind, uint64_t seed, uint64_t stream_id, const ckks_view *out, ckks_stream s) {
+static int sample_impl(ckks_ctx *c, int kind, const SampleKey &key, uint64_t stream_id, const ckks_view *out, ckks_stream s) {
     int rc;
     if ((rc = check_view(c, out, "destination"))) return rc;
     if (out->size != 1) return fail(CKKS_ERR_INVALID, "sample: destination must have size 1");
@@ -1330,11 +1341,27 @@ extern "C" int ckks_sample(ckks_ctx *c, int kind, uint64_t seed, uint64_t stream
     cudaStream_t st = (cudaStream_t)s;
     const dim3 grid((c->n + 255) / 256, out->batch);
     if (kind == 2) {
-        k_sample_uniform<<<grid, 256, 0, st>>>(dv(out), out->limbs, c->n, seed, stream_id, c->t);
+        k_sample_uniform<<<grid, 256, 0, st>>>(dv(out), out->limbs, c->n, key, stream_id, c->t);
         LAUNCH_CHECK(c);
         return CKKS_OK;   // uniform in the NTT domain is uniform
     }
-    k_sample_small<<<grid, 256, 0, st>>>(dv(out), out->limbs, c->n, kind, seed, stream_id, c->t);
+    k_sample_small<<<grid, 256, 0, st>>>(dv(out), out->limbs, c->n, kind, key, stream_id, c->t);
     LAUNCH_CHECK(c);
     return ntt_api(c, (uint64_t *)out->data, out->batch, out->limbs, 0, out->batch > 1 ? out->batch_stride : out->poly_stride, false, st);
+}
+
+// ChaCha20 under the caller's 256-bit key (32 bytes from a CSPRNG): the entry point KeyGenerator / Encryptor use
+extern "C" int ckks_sample_keyed(ckks_ctx *c, int kind, const uint8_t key[32], uint64_t stream_id, const ckks_view *out, ckks_stream s) {
+    if (!key) return fail(CKKS_ERR_INVALID, "sample: null key");
+    SampleKey k;
+    memcpy(k.k, key, 32);
+    return sample_impl(c, kind, k, stream_id, out, s);
+}
+// Reproducible sampling for tests and benchmarks: the 64-bit seed is expanded into the ChaCha20 key, so the output
+// has at most 64 bits of entropy -- NOT for real keys (use ckks_sample_keyed)
+extern "C" int ckks_sample(ckks_ctx *c, int kind, uint64_t seed, uint64_t stream_id, const ckks_view *out, ckks_stream s) {
+    SampleKey k;
+    uint64_t w[4] = {seed, ~seed, seed * 0x9E3779B97F4A7C15ull + 1, (seed ^ 0xD1B54A32D192ED03ull) * 0xBF58476D1CE4E5B9ull};
+    memcpy(k.k, w, 32);
+    return sample_impl(c, kind, k, stream_id, out, s);
 }

@@ -414,10 +414,16 @@ class Evaluator:
 
     def sample(self, kind, seed, stream_id, count, limbs):
         """count polynomials over primes [0, limbs) -> int64 CUDA tensor [count][limbs][N]; ternary and
-        normal (sigma 3.2, clipped) polynomials come back in NTT form"""
+        normal (sigma 3.2, clipped) polynomials come back in NTT form.  `seed`: 32 bytes from a CSPRNG (ChaCha20 key,
+        ckks_sample_keyed) or an int (reproducible test stream with at most 64 bits of entropy, ckks_sample)."""
         out = self.ctx.empty(count, 1, limbs)
         vo = out.view()
-        check(self.lib.ckks_sample(self.h, int(kind), int(seed) & (2 ** 64 - 1), int(stream_id), C.byref(vo), _stream()))
+        if isinstance(seed, (bytes, bytearray)):
+            if len(seed) != 32:
+                raise capi.CkksInvalidArgument("sample: the key must be 32 bytes")
+            check(self.lib.ckks_sample_keyed(self.h, int(kind), bytes(seed), int(stream_id), C.byref(vo), _stream()))
+        else:
+            check(self.lib.ckks_sample(self.h, int(kind), int(seed) & (2 ** 64 - 1), int(stream_id), C.byref(vo), _stream()))
         return out.data[:, 0]
 
     # ---- raw NTT (tests / encoder)

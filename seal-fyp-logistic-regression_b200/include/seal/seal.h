@@ -451,15 +451,32 @@ public:
 namespace detail {
 
 // thin wrappers: every ring operation goes through the GPU engine
-inline std::uint64_t fresh_seed() {
+// 256-bit generator key from the operating system's entropy source (std::random_device reads getrandom / /dev/urandom /
+// RDRAND on the supported platforms): the device-side sampler is ChaCha20 in counter mode under this key
+// (ckks_sample_keyed), i.e. a CSPRNG like SEAL 3.4.5's own default generator.
+struct SampleKey256 {
+    std::uint8_t b[32];
+};
+inline SampleKey256 fresh_key() {
     std::random_device rd;
-    return ((std::uint64_t)rd() << 32) ^ (std::uint64_t)rd();
+    SampleKey256 k;
+    for (int i = 0; i < 8; i++) {
+        const std::uint32_t w = rd();
+        std::memcpy(k.b + 4 * i, &w, 4);
+    }
+    return k;
+}
+inline void secure_zero(void *p, std::size_t bytes) {
+    volatile unsigned char *q = static_cast<volatile unsigned char *>(p);
+    while (bytes--) *q++ = 0;
 }
 
 struct Ring {
     std::shared_ptr<Engine> e;
-    std::uint64_t seed_, stream_ = 0;
-    explicit Ring(std::shared_ptr<Engine> eng, std::uint64_t seed) : e(std::move(eng)), seed_(seed) {}
+    SampleKey256 key_;
+    std::uint64_t stream_ = 0;
+    explicit Ring(std::shared_ptr<Engine> eng, const SampleKey256 &key) : e(std::move(eng)), key_(key) {}
+    ~Ring() { secure_zero(key_.b, sizeof(key_.b)); }
 
     ckks_view view(std::uint64_t *p, int batch, int size, int limbs) const {
         ckks_view v;
@@ -472,13 +489,13 @@ struct Ring {
         v.reserved = 0;
         return v;
     }
-    // Sampling runs on the device (ckks_sample): a counter-based generator keyed by this object's
-    // seed, one stream id per call.  count polynomials over primes [0, limbs): device [count][limbs][N];
+    // Sampling runs on the device (ckks_sample_keyed): ChaCha20 in counter mode keyed by this object's
+    // 256-bit key, one stream id (nonce) per call.  count polynomials over primes [0, limbs): device [count][limbs][N];
     // ternary and normal polynomials hold the same small integer in every limb and come back in NTT form.
     BufPtr draw(int kind, int count, int limbs) {
         auto b = std::make_shared<DevBuf>(e, (std::size_t)count * limbs * e->n);
         ckks_view v = view(b->p, count, 1, limbs);
-        check(ckks_sample(e->ctx, kind, seed_, ++stream_, &v, nullptr));
+        check(ckks_sample_keyed(e->ctx, kind, key_.b, ++stream_, &v, nullptr));
         return b;
     }
     BufPtr ternary_ntt(int count, int limbs) { return draw(CKKS_SAMPLE_TERNARY, count, limbs); }
@@ -511,7 +528,7 @@ struct Ring {
 class KeyGenerator {
 public:
     template <class Ctx>
-    explicit KeyGenerator(const Ctx &context) : ring_(detail::engine_of(context), detail::fresh_seed()) {
+    explicit KeyGenerator(const Ctx &context) : ring_(detail::engine_of(context), detail::fresh_key()) {
         auto &e = ring_.e;
         sk_.buf = ring_.ternary_ntt(1, e->K);
     }
@@ -563,6 +580,14 @@ public:
         gk.s = make_shared_keys();
         std::size_t n = e->n;
         std::vector<std::uint64_t> hsk((std::size_t)e->K * n), perm_sk(hsk.size());
+        // the host copies of the secret key are wiped on every exit path
+        struct Wipe {
+            std::vector<std::uint64_t> &a, &b;
+            ~Wipe() {
+                detail::secure_zero(a.data(), a.size() * 8);
+                detail::secure_zero(b.data(), b.size() * 8);
+            }
+        } wipe{hsk, perm_sk};
         detail::check(ckks_download(e->ctx, hsk.data(), sk_.buf->p, hsk.size() * 8, nullptr));
         detail::check(ckks_stream_sync(e->ctx, nullptr));
         for (std::uint64_t g : elts) {
@@ -700,7 +725,7 @@ private:
 class Encryptor {
 public:
     template <class Ctx>
-    Encryptor(const Ctx &context, const PublicKey &pk) : ring_(detail::engine_of(context), detail::fresh_seed()), pk_(pk) {}
+    Encryptor(const Ctx &context, const PublicKey &pk) : ring_(detail::engine_of(context), detail::fresh_key()), pk_(pk) {}
 
     // (u pk + e) one level above the plaintext's level, divided-and-rounded by the extra prime
     // (the rescale kernels), plus the plaintext in c0
@@ -737,7 +762,7 @@ private:
 class Decryptor {
 public:
     template <class Ctx>
-    Decryptor(const Ctx &context, const SecretKey &sk) : ring_(detail::engine_of(context), 0), sk_(sk) {}
+    Decryptor(const Ctx &context, const SecretKey &sk) : ring_(detail::engine_of(context), detail::SampleKey256{}), sk_(sk) {}   // draws nothing
 
     void decrypt(const Ciphertext &encrypted, Plaintext &dst) {
         auto &e = ring_.e;
