@@ -27,9 +27,11 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <istream>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <ostream>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -184,6 +186,9 @@ public:
     std::size_t poly_modulus_degree() const { return n_; }
     const std::vector<SmallModulus> &coeff_modulus() const { return coeff_; }
     const SmallModulus &plain_modulus() const { return plain_; }
+    // SEAL 3.4.x binary stream (uncompressed): see the serialization block at the end of this header
+    inline std::streamoff save(std::ostream &stream) const;
+    inline void load(std::istream &stream);
 
 private:
     scheme_type scheme_;
@@ -394,6 +399,9 @@ public:
     parms_id_type parms_id() const { return p_.parms_id(); }
     bool is_ntt_form() const { return true; }
     std::size_t coeff_count() const { return p_.eng ? (std::size_t)p_.limbs * p_.eng->n : 0; }
+    inline std::streamoff save(std::ostream &stream) const;
+    template <class Ctx>
+    inline void load(const Ctx &context, std::istream &stream);
     detail::Poly &poly() { return p_; }
     const detail::Poly &poly() const { return p_; }
 
@@ -411,6 +419,9 @@ public:
     std::size_t coeff_mod_count() const { return (std::size_t)p_.limbs; }
     std::size_t poly_modulus_degree() const { return p_.eng ? p_.eng->n : 0; }
     bool is_ntt_form() const { return true; }
+    inline std::streamoff save(std::ostream &stream) const;
+    template <class Ctx>
+    inline void load(const Ctx &context, std::istream &stream);
     detail::Poly &poly() { return p_; }
     const detail::Poly &poly() const { return p_; }
 
@@ -421,10 +432,12 @@ private:
 class SecretKey {
 public:
     detail::BufPtr buf;   // [K][N], NTT form
+    inline std::streamoff save(std::ostream &stream) const;
 };
 class PublicKey {
 public:
     detail::BufPtr buf;   // [2][K][N]
+    inline std::streamoff save(std::ostream &stream) const;
 };
 
 class KSwitchKeys {
@@ -439,10 +452,22 @@ public:
     };
     std::shared_ptr<Shared> s;   // copies of RelinKeys / GaloisKeys share device storage
     std::size_t size() const { return s ? s->keys.size() : 0; }
+
+protected:
+    inline std::streamoff save_impl(std::ostream &stream, bool galois) const;
+    inline void load_impl(std::shared_ptr<detail::Engine> eng, std::istream &stream, bool galois);
 };
-class RelinKeys : public KSwitchKeys {};
+class RelinKeys : public KSwitchKeys {
+public:
+    std::streamoff save(std::ostream &stream) const { return save_impl(stream, false); }
+    template <class Ctx>
+    inline void load(const Ctx &context, std::istream &stream);
+};
 class GaloisKeys : public KSwitchKeys {
 public:
+    std::streamoff save(std::ostream &stream) const { return save_impl(stream, true); }
+    template <class Ctx>
+    inline void load(const Ctx &context, std::istream &stream);
     bool has_key(std::uint64_t galois_elt) const { return s && s->keys.count(galois_elt); }
     static std::size_t get_index(std::uint64_t galois_elt) { return (std::size_t)((galois_elt - 1) >> 1); }
 };
@@ -1027,4 +1052,362 @@ private:
     std::shared_ptr<detail::Engine> e_;
 };
 
+// ------------------------------------------------------------------------------------ serialization
+// SEAL 3.4.x binary streams, uncompressed (compr_mode none; SEAL reads those whatever its own default is):
+//   object = { uint16 magic 0xA15E, uint8 0, uint8 compr_mode, uint32 size } + body, nested objects carry their own header.
+// Layouts per class: seal-fyp-logistic-regression_b200/sealio.py (the Python reader/writer of the same format; tools/seal_replay.py
+// replays files written by a real SEAL build on this engine).  Data is SEAL's in-memory layout, which is also the
+// engine's, so save/load are a header plus one device <-> host copy.
+namespace detail {
+inline void io_write(std::ostream &o, const void *p, std::size_t n) {
+    o.write(static_cast<const char *>(p), (std::streamsize)n);
+    if (!o) throw std::runtime_error("I/O error");
+}
+template <class T>
+inline void io_pod(std::string &b, T v) { b.append(reinterpret_cast<const char *>(&v), sizeof(T)); }
+inline std::string io_object(const std::string &body) {
+    std::string out;
+    io_pod<std::uint16_t>(out, 0xA15E);
+    io_pod<std::uint8_t>(out, 0);
+    io_pod<std::uint8_t>(out, 0);   // compr_mode_type::none
+    io_pod<std::uint32_t>(out, (std::uint32_t)(8 + body.size()));
+    out += body;
+    return out;
+}
+// reads one object (3.4 header, or the 16-byte header of 3.5+) -> body; compressed streams are refused (no zlib here)
+inline std::string io_read_object(std::istream &in) {
+    unsigned char h[16];
+    in.read(reinterpret_cast<char *>(h), 4);
+    if (!in || h[0] != 0x5E || h[1] != 0xA1) throw std::logic_error("loaded SEALHeader is invalid");
+    std::uint64_t size, hdr;
+    std::uint8_t compr;
+    if (h[2] == 0x00) {
+        compr = h[3];
+        std::uint32_t s32;
+        in.read(reinterpret_cast<char *>(&s32), 4);
+        size = s32;
+        hdr = 8;
+    } else if (h[2] == 0x10) {
+        in.read(reinterpret_cast<char *>(h + 4), 12);
+        compr = h[5];
+        std::memcpy(&size, h + 8, 8);
+        hdr = 16;
+    } else {
+        throw std::logic_error("loaded SEALHeader is invalid");
+    }
+    if (!in || size < hdr) throw std::logic_error("loaded SEALHeader is invalid");
+    if (compr != 0) throw std::logic_error("unsupported compression mode (save with compr_mode_type::none)");
+    std::string body((std::size_t)(size - hdr), '\0');
+    in.read(&body[0], (std::streamsize)body.size());
+    if (!in) throw std::runtime_error("I/O error");
+    return body;
+}
+struct IoCursor {
+    const std::string &b;
+    std::size_t off = 0;
+    template <class T>
+    T pod() {
+        if (off + sizeof(T) > b.size()) throw std::logic_error("loaded data is invalid");
+        T v;
+        std::memcpy(&v, b.data() + off, sizeof(T));
+        off += sizeof(T);
+        return v;
+    }
+    std::string object() {   // nested object
+        struct View : std::streambuf {
+            View(const char *p, std::size_t n) { setg(const_cast<char *>(p), const_cast<char *>(p), const_cast<char *>(p) + n); }
+            std::size_t used() const { return (std::size_t)(gptr() - eback()); }
+        } sb(b.data() + off, b.size() - off);
+        std::istream in(&sb);
+        std::string body = io_read_object(in);
+        off += sb.used();
+        return body;
+    }
+};
+// SHA3-256 (FIPS 202): SEAL 3.4.x hashes the parameter words with it to form parms_id
+inline void sha3_256(const std::uint8_t *msg, std::size_t len, std::uint8_t out[32]) {
+    static const std::uint64_t RC[24] = {
+        0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull, 0x000000000000808bull,
+        0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008aull, 0x0000000000000088ull,
+        0x0000000080008009ull, 0x000000008000000aull, 0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull,
+        0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+        0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+    static const int ROT[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+    static const int PIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    std::uint64_t st[25] = {0};
+    auto permute = [&]() {
+        for (int r = 0; r < 24; r++) {
+            std::uint64_t bc[5];
+            for (int i = 0; i < 5; i++) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
+            for (int i = 0; i < 5; i++) {
+                std::uint64_t t = bc[(i + 4) % 5] ^ ((bc[(i + 1) % 5] << 1) | (bc[(i + 1) % 5] >> 63));
+                for (int j = 0; j < 25; j += 5) st[j + i] ^= t;
+            }
+            std::uint64_t t = st[1];
+            for (int i = 0; i < 24; i++) {
+                int j = PIL[i];
+                std::uint64_t b = st[j];
+                st[j] = (t << ROT[i]) | (t >> (64 - ROT[i]));
+                t = b;
+            }
+            for (int j = 0; j < 25; j += 5) {
+                std::uint64_t row[5];
+                for (int i = 0; i < 5; i++) row[i] = st[j + i];
+                for (int i = 0; i < 5; i++) st[j + i] ^= (~row[(i + 1) % 5]) & row[(i + 2) % 5];
+            }
+            st[0] ^= RC[r];
+        }
+    };
+    const std::size_t rate = 136;
+    std::vector<std::uint8_t> buf(msg, msg + len);
+    buf.push_back(0x06);
+    while (buf.size() % rate) buf.push_back(0);
+    buf.back() |= 0x80;
+    for (std::size_t off = 0; off < buf.size(); off += rate) {
+        for (std::size_t i = 0; i < rate / 8; i++) {
+            std::uint64_t w;
+            std::memcpy(&w, buf.data() + off + 8 * i, 8);
+            st[i] ^= w;
+        }
+        permute();
+    }
+    std::memcpy(out, st, 32);
+}
+// SEAL's parms_id of the level with `limbs` primes: SHA3-256 over {scheme, N, q_0 .. q_{limbs-1}, plain_modulus = 0}
+inline parms_id_type seal_parms_id(const Engine &e, int limbs) {
+    std::vector<std::uint64_t> w{(std::uint64_t)scheme_type::CKKS, (std::uint64_t)e.n};
+    for (int j = 0; j < limbs; j++) w.push_back(e.primes[j]);
+    w.push_back(0);
+    std::uint8_t dig[32];
+    sha3_256(reinterpret_cast<const std::uint8_t *>(w.data()), w.size() * 8, dig);
+    parms_id_type id;
+    std::memcpy(id.data(), dig, 32);
+    return id;
+}
+// body of a Ciphertext object over device words [size][cap][N] (active limbs only)
+inline std::string io_ct_body(const std::shared_ptr<Engine> &e, const std::uint64_t *dev, int size, int limbs, int cap, double scale) {
+    const std::size_t n = e->n;
+    std::vector<std::uint64_t> host((std::size_t)size * limbs * n);
+    for (int s = 0; s < size; s++)
+        check(ckks_download(e->ctx, host.data() + (std::size_t)s * limbs * n, dev + (std::size_t)s * cap * n, (std::size_t)limbs * n * 8, nullptr));
+    check(ckks_stream_sync(e->ctx, nullptr));
+    std::string b;
+    const parms_id_type id = seal_parms_id(*e, limbs);
+    b.append(reinterpret_cast<const char *>(id.data()), 32);
+    io_pod<std::uint8_t>(b, 1);   // is_ntt_form
+    io_pod<std::uint64_t>(b, (std::uint64_t)size);
+    io_pod<std::uint64_t>(b, (std::uint64_t)n);
+    io_pod<std::uint64_t>(b, (std::uint64_t)limbs);
+    io_pod<double>(b, scale);
+    std::string arr;
+    io_pod<std::uint64_t>(arr, (std::uint64_t)host.size());
+    arr.append(reinterpret_cast<const char *>(host.data()), host.size() * 8);
+    b += io_object(arr);
+    return b;
+}
+// parses a Ciphertext body into host words; returns {size, limbs, scale}
+struct IoCt {
+    int size = 0, limbs = 0;
+    double scale = 1.0;
+    std::vector<std::uint64_t> words;
+};
+inline IoCt io_parse_ct(const std::string &body, const Engine &e) {
+    IoCursor c{body};
+    c.off = 32;   // parms_id: the level is taken from coeff_mod_count (ids are hashes of the same information)
+    IoCt r;
+    (void)c.pod<std::uint8_t>();
+    r.size = (int)c.pod<std::uint64_t>();
+    const std::uint64_t n = c.pod<std::uint64_t>();
+    r.limbs = (int)c.pod<std::uint64_t>();
+    r.scale = c.pod<double>();
+    if (n != e.n || r.limbs < 1 || r.limbs > e.K || r.size < 1 || r.size > 3) throw std::logic_error("ciphertext data is invalid");
+    std::string arr = c.object();
+    IoCursor a{arr};
+    const std::uint64_t cnt = a.pod<std::uint64_t>();
+    if (cnt != (std::uint64_t)r.size * r.limbs * n || arr.size() != 8 + cnt * 8) throw std::logic_error("ciphertext data is invalid");
+    r.words.resize(cnt);
+    std::memcpy(r.words.data(), arr.data() + 8, cnt * 8);
+    for (int s = 0; s < r.size; s++)
+        for (int j = 0; j < r.limbs; j++)
+            for (std::uint64_t i = 0; i < n; i++)
+                if (r.words[((std::size_t)s * r.limbs + j) * n + i] >= e.primes[j]) throw std::logic_error("ciphertext data is invalid");
+    return r;
+}
+}  // namespace detail
+
+inline std::streamoff EncryptionParameters::save(std::ostream &stream) const {
+    std::string b;
+    detail::io_pod<std::uint8_t>(b, (std::uint8_t)scheme_);
+    detail::io_pod<std::uint64_t>(b, (std::uint64_t)n_);
+    detail::io_pod<std::uint64_t>(b, (std::uint64_t)coeff_.size());
+    auto mod = [](std::uint64_t v) {
+        std::string m;
+        detail::io_pod<std::uint64_t>(m, v);
+        return detail::io_object(m);
+    };
+    for (const auto &q : coeff_) b += mod(q.value());
+    b += mod(plain_.value());
+    const std::string out = detail::io_object(b);
+    detail::io_write(stream, out.data(), out.size());
+    return (std::streamoff)out.size();
+}
+inline void EncryptionParameters::load(std::istream &stream) {
+    const std::string body = detail::io_read_object(stream);
+    detail::IoCursor c{body};
+    scheme_ = (scheme_type)c.pod<std::uint8_t>();
+    n_ = (std::size_t)c.pod<std::uint64_t>();
+    const std::uint64_t cnt = c.pod<std::uint64_t>();
+    if (cnt > 64) throw std::logic_error("coeff_modulus is invalid");
+    coeff_.clear();
+    for (std::uint64_t i = 0; i <= cnt; i++) {
+        const std::string m = c.object();
+        if (m.size() != 8) throw std::logic_error("SmallModulus is invalid");
+        std::uint64_t v;
+        std::memcpy(&v, m.data(), 8);
+        if (i < cnt) coeff_.push_back(SmallModulus(v));
+        else plain_ = SmallModulus(v);
+    }
+}
+
+inline std::streamoff Ciphertext::save(std::ostream &stream) const {
+    if (!p_.buf) throw std::logic_error("cannot save an empty ciphertext");
+    const std::string out = detail::io_object(detail::io_ct_body(p_.eng, p_.buf->p, p_.size, p_.limbs, p_.cap, p_.scale));
+    detail::io_write(stream, out.data(), out.size());
+    return (std::streamoff)out.size();
+}
+template <class Ctx>
+inline void Ciphertext::load(const Ctx &context, std::istream &stream) {
+    auto e = detail::engine_of(context);
+    const detail::IoCt r = detail::io_parse_ct(detail::io_read_object(stream), *e);
+    if (r.limbs > e->K - 1) throw std::logic_error("ciphertext data is invalid");
+    p_.allocate(e, r.size, r.limbs);
+    p_.scale = r.scale;
+    detail::check(ckks_upload(e->ctx, p_.buf->p, r.words.data(), r.words.size() * 8, nullptr));
+    detail::check(ckks_stream_sync(e->ctx, nullptr));
+}
+
+inline std::streamoff Plaintext::save(std::ostream &stream) const {
+    if (!p_.buf) throw std::logic_error("cannot save an empty plaintext");
+    auto &e = p_.eng;
+    const std::size_t n = e->n;
+    std::vector<std::uint64_t> host((std::size_t)p_.limbs * n);
+    detail::check(ckks_download(e->ctx, host.data(), p_.buf->p, host.size() * 8, nullptr));
+    detail::check(ckks_stream_sync(e->ctx, nullptr));
+    std::string b;
+    const parms_id_type id = detail::seal_parms_id(*e, p_.limbs);
+    b.append(reinterpret_cast<const char *>(id.data()), 32);
+    detail::io_pod<double>(b, p_.scale);
+    std::string arr;
+    detail::io_pod<std::uint64_t>(arr, (std::uint64_t)host.size());
+    arr.append(reinterpret_cast<const char *>(host.data()), host.size() * 8);
+    b += detail::io_object(arr);
+    const std::string out = detail::io_object(b);
+    detail::io_write(stream, out.data(), out.size());
+    return (std::streamoff)out.size();
+}
+template <class Ctx>
+inline void Plaintext::load(const Ctx &context, std::istream &stream) {
+    auto e = detail::engine_of(context);
+    const std::string body = detail::io_read_object(stream);
+    detail::IoCursor c{body};
+    c.off = 32;
+    const double scale = c.pod<double>();
+    const std::string arr = c.object();
+    detail::IoCursor a{arr};
+    const std::uint64_t cnt = a.pod<std::uint64_t>();
+    if (cnt == 0 || cnt % e->n || cnt / e->n > (std::uint64_t)e->K || arr.size() != 8 + cnt * 8) throw std::logic_error("plaintext data is invalid");
+    p_.allocate(e, 1, (int)(cnt / e->n));
+    p_.scale = scale;
+    detail::check(ckks_upload(e->ctx, p_.buf->p, arr.data() + 8, cnt * 8, nullptr));
+    detail::check(ckks_stream_sync(e->ctx, nullptr));
+}
+
+inline std::streamoff PublicKey::save(std::ostream &stream) const {
+    if (!buf) throw std::logic_error("cannot save an empty key");
+    auto &e = buf->eng;
+    const std::string out = detail::io_object(detail::io_object(detail::io_ct_body(e, buf->p, 2, e->K, e->K, 1.0)));
+    detail::io_write(stream, out.data(), out.size());
+    return (std::streamoff)out.size();
+}
+inline std::streamoff SecretKey::save(std::ostream &stream) const {
+    if (!buf) throw std::logic_error("cannot save an empty key");
+    auto &e = buf->eng;
+    std::vector<std::uint64_t> host((std::size_t)e->K * e->n);
+    detail::check(ckks_download(e->ctx, host.data(), buf->p, host.size() * 8, nullptr));
+    detail::check(ckks_stream_sync(e->ctx, nullptr));
+    std::string b;
+    const parms_id_type id = detail::seal_parms_id(*e, e->K);
+    b.append(reinterpret_cast<const char *>(id.data()), 32);
+    detail::io_pod<double>(b, 1.0);
+    std::string arr;
+    detail::io_pod<std::uint64_t>(arr, (std::uint64_t)host.size());
+    arr.append(reinterpret_cast<const char *>(host.data()), host.size() * 8);
+    detail::secure_zero(host.data(), host.size() * 8);
+    b += detail::io_object(arr);
+    const std::string out = detail::io_object(detail::io_object(b));   // SecretKey wraps a Plaintext
+    detail::io_write(stream, out.data(), out.size());
+    return (std::streamoff)out.size();
+}
+
+inline std::streamoff KSwitchKeys::save_impl(std::ostream &stream, bool galois) const {
+    if (!s || s->keys.empty()) throw std::logic_error("cannot save empty keys");
+    auto &e = s->eng;
+    const int K = e->K;
+    const std::size_t kw = (std::size_t)2 * K * e->n;   // words of one decomposition digit
+    std::string b;
+    const parms_id_type id = detail::seal_parms_id(*e, K);
+    b.append(reinterpret_cast<const char *>(id.data()), 32);
+    const std::uint64_t dim1 = galois ? (std::uint64_t)e->n : 1;   // SEAL sizes GaloisKeys::keys_ to coeff_count
+    detail::io_pod<std::uint64_t>(b, dim1);
+    std::map<std::uint64_t, detail::BufPtr> by_index;
+    for (auto &kv : s->keys) by_index[galois ? (kv.first - 1) >> 1 : 0] = kv.second;
+    for (std::uint64_t idx = 0; idx < dim1; idx++) {
+        auto it = by_index.find(idx);
+        if (it == by_index.end()) {
+            detail::io_pod<std::uint64_t>(b, 0);
+            continue;
+        }
+        detail::io_pod<std::uint64_t>(b, (std::uint64_t)(K - 1));
+        for (int d = 0; d < K - 1; d++)   // each digit: a PublicKey object wrapping a size-2 ciphertext at the key level
+            b += detail::io_object(detail::io_object(detail::io_ct_body(e, it->second->p + (std::size_t)d * kw, 2, K, K, 1.0)));
+    }
+    const std::string out = detail::io_object(b);
+    detail::io_write(stream, out.data(), out.size());
+    return (std::streamoff)out.size();
+}
+inline void KSwitchKeys::load_impl(std::shared_ptr<detail::Engine> e, std::istream &stream, bool galois) {
+    const std::string body = detail::io_read_object(stream);
+    detail::IoCursor c{body};
+    c.off = 32;
+    const std::uint64_t dim1 = c.pod<std::uint64_t>();
+    const int K = e->K;
+    const std::size_t kw = (std::size_t)2 * K * e->n;
+    s = std::make_shared<Shared>();
+    s->eng = e;
+    detail::check(ckks_keyset_create(e->ctx, &s->ks));
+    for (std::uint64_t idx = 0; idx < dim1; idx++) {
+        const std::uint64_t dim2 = c.pod<std::uint64_t>();
+        if (dim2 == 0) continue;
+        if (dim2 != (std::uint64_t)(K - 1)) throw std::logic_error("key-switching key data is invalid");
+        auto d = std::make_shared<detail::DevBuf>(e, (std::size_t)(K - 1) * kw);
+        for (int j = 0; j < K - 1; j++) {
+            const std::string pk = c.object();
+            detail::IoCursor pc{pk};
+            const detail::IoCt ct = detail::io_parse_ct(pc.object(), *e);
+            if (ct.size != 2 || ct.limbs != K) throw std::logic_error("key-switching key data is invalid");
+            detail::check(ckks_upload(e->ctx, d->p + (std::size_t)j * kw, ct.words.data(), kw * 8, nullptr));
+            detail::check(ckks_stream_sync(e->ctx, nullptr));
+        }
+        const std::uint64_t g = galois ? 2 * idx + 1 : 0;
+        s->keys[g] = d;
+        if (galois) detail::check(ckks_keyset_set_galois(s->ks, g, d->p));
+        else detail::check(ckks_keyset_set_relin(s->ks, d->p));
+    }
+}
+template <class Ctx>
+inline void RelinKeys::load(const Ctx &context, std::istream &stream) { load_impl(detail::engine_of(context), stream, false); }
+template <class Ctx>
+inline void GaloisKeys::load(const Ctx &context, std::istream &stream) { load_impl(detail::engine_of(context), stream, true); }
+
 }  // namespace seal
+
