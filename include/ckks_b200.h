@@ -64,8 +64,10 @@ void ckks_ctx_destroy(ckks_ctx *ctx);
 int ckks_ctx_log_n(const ckks_ctx *ctx);
 int ckks_ctx_n_primes(const ckks_ctx *ctx);
 uint64_t ckks_ctx_prime(const ckks_ctx *ctx, int j);
-/* 1 = divide-and-round (SEAL 3.4.5), 0 = floor; see SURVEY.md A.7/A.8 */
-int ckks_ctx_set_rounding(ckks_ctx *ctx, int round_half);
+/* the two divide-by-last-prime steps (SURVEY.md A.7 key-switch mod-down, A.8 rescale; both marked unconfirmed against a real
+ * SEAL 3.4.5 build there): mode 0 = floor in both, 1 = round to nearest in both (default), 2 = key switch rounds / rescale
+ * floors, 3 = key switch floors / rescale rounds.  tools/seal_replay.py on files written by real SEAL decides. */
+int ckks_ctx_set_rounding(ckks_ctx *ctx, int mode);
 /* cap (bytes) on the internal key-switch workspace; larger batches are processed in chunks */
 int ckks_ctx_set_workspace_cap(ckks_ctx *ctx, size_t bytes);
 /* number of concurrent half-/quarter-batch pipelines a rotate-and-sum chain is split into (1..4, default 2) */

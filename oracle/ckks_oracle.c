@@ -230,7 +230,7 @@ orc_ctx *orc_create(int log_n, int n_primes, const u64 *primes) {
     c->log_n = log_n;
     c->n = (size_t)1 << log_n;
     c->K = n_primes;
-    c->round_half = 1;
+    c->round_half = 3;   /* bit 0: key-switch mod-down rounds to nearest, bit 1: rescale does */
     c->m = calloc((size_t)n_primes, sizeof(orc_mod));
     size_t n = c->n;
     for (int j = 0; j < n_primes; j++) {
@@ -287,7 +287,9 @@ void orc_destroy(orc_ctx *c) {
     free(c->m); free(c->slot_map); free(c->root_re); free(c->root_im);
     free(c);
 }
-void orc_set_rounding(orc_ctx *c, int round_half) { c->round_half = round_half; }
+/* mode: 0 = floor everywhere, 1 = round to nearest everywhere (default), 2 = key switch rounds / rescale floors,
+ * 3 = key switch floors / rescale rounds */
+void orc_set_rounding(orc_ctx *c, int mode) { c->round_half = mode == 0 ? 0 : mode == 1 ? 3 : mode == 2 ? 1 : 2; }
 u64 orc_prime(const orc_ctx *c, int j) { return c->m[j].p; }
 u64 orc_psi(const orc_ctx *c, int j) { return c->m[j].psi; }
 int orc_log_n(const orc_ctx *c) { return c->log_n; }
@@ -444,10 +446,10 @@ int orc_is_transparent(const orc_ctx *c, int S, int L, const u64 *ct) {
  * given r = INTT(last limb) in [0,qk) (coefficient form), produce for data prime j the NTT of
  *   u_j = ((r + half) mod qk) mod q_j - (half mod q_j)      (rounding; half = qk >> 1)
  * or u_j = r mod q_j when rounding is off.  `work` is one limb of scratch. */
-static void last_limb_to(const orc_ctx *c, int jk, int j, const u64 *r, u64 *work) {
+static void last_limb_to(const orc_ctx *c, int jk, int j, const u64 *r, u64 *work, int do_round) {
     const orc_mod *mk = &c->m[jk], *mj = &c->m[j];
     size_t n = c->n;
-    u64 half = c->round_half ? (mk->p >> 1) : 0;
+    u64 half = do_round ? (mk->p >> 1) : 0;
     u64 half_j = reduce64(half, mj);
     for (size_t q = 0; q < n; q++) {
         u64 v = r[q] + half;
@@ -470,7 +472,7 @@ void orc_rescale(const orc_ctx *c, int S, int L, const u64 *in, u64 *out) {
         for (int j = 0; j < L - 1; j++) {
             const orc_mod *mj = &c->m[j];
             u64 inv = invmod(c->m[jk].p % mj->p, mj->p);
-            last_limb_to(c, jk, j, r, work);
+            last_limb_to(c, jk, j, r, work, c->round_half & 2);
             const u64 *x = in + ((size_t)s * L + j) * n;
             u64 *z = out + ((size_t)s * (L - 1) + j) * n;
             for (size_t q = 0; q < n; q++) z[q] = mulmod(submod(x[q], work[q], mj->p), inv, mj);
@@ -536,7 +538,7 @@ void orc_switch_key(const orc_ctx *c, int L, u64 *ct, const u64 *target, const u
         for (int j = 0; j < L; j++) {
             const orc_mod *mj = &c->m[j];
             u64 pinv = invmod(mP->p % mj->p, mj->p);
-            last_limb_to(c, jP, j, r, work);
+            last_limb_to(c, jP, j, r, work, c->round_half & 1);
             u128 *a = acc + ((size_t)k * R + j) * n;
             u64 *z = ct + ((size_t)k * L + j) * n;
             for (size_t q = 0; q < n; q++) {

@@ -42,8 +42,10 @@ int orc_is_prime(uint64_t v);
 /* ---- context */
 orc_ctx *orc_create(int log_n, int n_primes, const uint64_t *primes);
 void orc_destroy(orc_ctx *c);
-/* rounding switch for divide-by-last-prime (1 = SEAL 3.4.5 round-to-nearest, 0 = floor) */
-void orc_set_rounding(orc_ctx *c, int round_half);
+/* rounding switch for the two divide-by-last-prime steps (both marked unconfirmed there):
+ * 0 = floor in both, 1 = round to nearest in both (default), 2 = key-switch mod-down rounds / rescale floors,
+ * 3 = key-switch mod-down floors / rescale rounds.  tools/seal_replay.py against real SEAL files decides. */
+void orc_set_rounding(orc_ctx *c, int mode);
 uint64_t orc_prime(const orc_ctx *c, int j);
 uint64_t orc_psi(const orc_ctx *c, int j);      /* minimal primitive 2N-th root */
 int orc_log_n(const orc_ctx *c);

@@ -184,7 +184,7 @@ class Oracle:
             self._h = None
 
     def set_rounding(self, on):
-        lib().orc_set_rounding(self._h, 1 if on else 0)
+        lib().orc_set_rounding(self._h, int(on))   # 0 floor, 1/True round, 2 round key switch only, 3 round rescale only
 
     def psi(self, j):
         return int(lib().orc_psi(self._h, j))

@@ -95,6 +95,7 @@ struct ckks_ctx {
         cudaEvent_t fork = nullptr, join = nullptr, begin = nullptr, end = nullptr;
     } lane[4];
     int chain_lanes = 2;
+    int round_rescale = 1;     // divide-and-round (1) or floor (0) in rescale; t.round_half is the key switch's switch
     int fuse = 1;              // fused column passes / INTT-in-MAC (CKKS_FUSE=0 selects the unfused round-1 pipeline)
     int split1 = 0, split3 = 0; // forced nsplit of the fused column kernels (0 = heuristic)
     struct ChainGraph {
@@ -220,8 +221,12 @@ extern "C" void ckks_ctx_destroy(ckks_ctx *c) {
 extern "C" int ckks_ctx_log_n(const ckks_ctx *c) { return c->log_n; }
 extern "C" int ckks_ctx_n_primes(const ckks_ctx *c) { return c->K; }
 extern "C" uint64_t ckks_ctx_prime(const ckks_ctx *c, int j) { return (j >= 0 && j < c->K) ? c->primes[j] : 0; }
-extern "C" int ckks_ctx_set_rounding(ckks_ctx *c, int r) {
-    c->t.round_half = r ? 1 : 0;
+extern "C" int ckks_ctx_set_rounding(ckks_ctx *c, int mode) {
+    if (mode < 0 || mode > 3) return fail(CKKS_ERR_INVALID, "rounding mode must be 0..3");
+    c->t.round_half = (mode == 1 || mode == 2) ? 1 : 0;     // key-switch mod-down
+    c->round_rescale = (mode == 1 || mode == 3) ? 1 : 0;    // rescale
+    for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);   // captured kernels carry the flag by value
+    c->chain_graphs.clear();
     return CKKS_OK;
 }
 extern "C" int ckks_ctx_set_chain_lanes(ckks_ctx *c, int lanes) {
@@ -1134,6 +1139,8 @@ extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *o
     while ((long)Bc * S > 65535) Bc--;
     if ((rc = ensure_ws(c, per * 8 * Bc))) return rc;
     u64 *R = c->ws, *T2 = R + (size_t)Bc * S * N;
+    Tables tr = c->t;
+    tr.round_half = c->round_rescale;
     for (int b0 = 0; b0 < B; b0 += Bc) {
         const int bc = (B - b0) < Bc ? (B - b0) : Bc;
         DView src{(u64 *)in->data + (u64)b0 * in->batch_stride, in->batch_stride, in->poly_stride};
@@ -1146,19 +1153,19 @@ extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *o
 #define RUN(LN)                                                                                                   \
     {                                                                                                             \
         typedef NttGeo<LN> G;                                                                                     \
-        k_inv_row<LN><<<dim3(G::ROW_TILES, S, bc), NTT_THREADS, 0, st>>>(last, dR, 1, Lo, c->t);                  \
+        k_inv_row<LN><<<dim3(G::ROW_TILES, S, bc), NTT_THREADS, 0, st>>>(last, dR, 1, Lo, tr);                  \
         LAUNCH_CHECK(c);                                                                                          \
         if (c->fuse) {                                                                                            \
             const int ns3 = pick_split(c->split3, G::COL_TILES * S * bc, Lo);                                     \
-            launch_pdl(k_md_invcol_fwdcol<LN>, dim3(G::COL_TILES, ns3, bc * S), st, Rz, T2, Lo, Lo, ns3, c->t);   \
+            launch_pdl(k_md_invcol_fwdcol<LN>, dim3(G::COL_TILES, ns3, bc * S), st, Rz, T2, Lo, Lo, ns3, tr);   \
             LAUNCH_CHECK(c);                                                                                      \
         } else {                                                                                                  \
-            launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, S, bc), st, dR, dR, 1, Lo, c->t);          \
+            launch_pdl(k_inv_col<LN, true>, dim3(G::COL_TILES, S, bc), st, dR, dR, 1, Lo, tr);          \
             LAUNCH_CHECK(c);                                                                                      \
-            launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, Lo, bc * S), st, Rz, T2, Lo, Lo, c->t);       \
+            launch_pdl(k_md_fwd_col<LN>, dim3(G::COL_TILES, Lo, bc * S), st, Rz, T2, Lo, Lo, tr);       \
             LAUNCH_CHECK(c);                                                                                      \
         }                                                                                                         \
-        launch_pdl(k_md_fwd_row<LN, 0>, dim3(G::ROW_TILES, Lo, bc * S), st, T2, src, rrt, S, Lo, Lo, c->t); \
+        launch_pdl(k_md_fwd_row<LN, 0>, dim3(G::ROW_TILES, Lo, bc * S), st, T2, src, rrt, S, Lo, Lo, tr); \
         LAUNCH_CHECK(c);                                                                                          \
     }
         DISPATCH_LOGN(c, RUN)

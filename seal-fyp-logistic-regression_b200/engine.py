@@ -61,8 +61,9 @@ class Context:
             q *= p
         return q.bit_length()
 
-    def set_rounding(self, on):
-        check(self.lib.ckks_ctx_set_rounding(self._h, 1 if on else 0))
+    def set_rounding(self, mode):
+        """0 / False floor, 1 / True round (default), 2 round in key switching only, 3 round in rescale only"""
+        check(self.lib.ckks_ctx_set_rounding(self._h, int(mode)))
 
     def set_workspace_cap(self, nbytes):
         check(self.lib.ckks_ctx_set_workspace_cap(self._h, int(nbytes)))

@@ -153,18 +153,29 @@ def test_rescale_bit_exact(make_fixture, log_n):
 
 
 def test_rounding_switch_matches_oracle(make_fixture):
+    """the two unconfirmed SEAL conventions (round vs floor in the key switch's mod-down and in rescale) can be flipped
+    independently, on the engine and on the oracle alike; every combination stays bit-exact, and each switch changes
+    exactly the op it names"""
     fx = make_fixture(12, CHAINS[12])
     rng = np.random.default_rng(25)
     a = fx.random_ct(rng, 1, 2, fx.L)
     a3 = fx.random_ct(rng, 1, 3, fx.L)
+    seen = {}
     try:
-        fx.ctx.set_rounding(False)
-        fx.orc.set_rounding(False)
-        assert np.array_equal(fx.ev.rescale_to_next(fx.ctx.upload(a)).numpy()[0], fx.orc.rescale(a[0]))
-        assert np.array_equal(fx.ev.relinearize(fx.ctx.upload(a3), fx.keys).numpy()[0], fx.orc.relinearize(a3[0], fx.rlk))
+        for mode in (0, 1, 2, 3):
+            fx.ctx.set_rounding(mode)
+            fx.orc.set_rounding(mode)
+            rs = fx.ev.rescale_to_next(fx.ctx.upload(a)).numpy()[0]
+            rl = fx.ev.relinearize(fx.ctx.upload(a3), fx.keys).numpy()[0]
+            assert np.array_equal(rs, fx.orc.rescale(a[0])), mode
+            assert np.array_equal(rl, fx.orc.relinearize(a3[0], fx.rlk)), mode
+            seen[mode] = (rs, rl)
     finally:
-        fx.ctx.set_rounding(True)
-        fx.orc.set_rounding(True)
+        fx.ctx.set_rounding(1)
+        fx.orc.set_rounding(1)
+    assert np.array_equal(seen[1][0], seen[3][0]) and np.array_equal(seen[0][0], seen[2][0])     # rescale: modes 1, 3 round
+    assert np.array_equal(seen[1][1], seen[2][1]) and np.array_equal(seen[0][1], seen[3][1])     # key switch: modes 1, 2 round
+    assert not np.array_equal(seen[0][0], seen[1][0]) and not np.array_equal(seen[0][1], seen[1][1])
 
 
 def test_batched_equals_single_and_chunked_workspace(make_fixture):

@@ -32,9 +32,10 @@ def _load(path, fn, *a):
 class OracleBackend:
     name = "oracle"
 
-    def __init__(self, p, rlk, gks):
+    def __init__(self, p, rlk, gks, rounding=1):
         from oracle import pyoracle as po
         self.o = po.Oracle(p.log_n, p.primes)
+        self.o.set_rounding(rounding)
         self.rlk, self.gks = rlk, gks
 
     def add(self, a, b): return self.o.add(a, b)
@@ -50,10 +51,11 @@ class OracleBackend:
 class CudaBackend:
     name = "cuda"
 
-    def __init__(self, p, rlk, gks):
+    def __init__(self, p, rlk, gks, rounding=1):
         eng = importlib.import_module(PKG).load_engine()
         self.eng = eng
         self.ctx = eng.Context(p.log_n, p.primes)
+        self.ctx.set_rounding(rounding)
         self.ev = eng.Evaluator(self.ctx)
         self.keys = eng.KeySet(self.ctx)
         self.keys.set_relin(self.ctx.upload_key(rlk))
@@ -74,7 +76,7 @@ class CudaBackend:
     def mod_switch(self, a): return self.ev.mod_switch_to(self._up(a), a.shape[1] - 1).numpy()[0]
 
 
-def replay(d, backends):
+def replay(d, backends, rounding=1):
     p = _load(os.path.join(d, "parms.bin"), sio.load_params)
     n = p.n
     rlk = _load(os.path.join(d, "relin_keys.bin"), sio.load_kswitch_keys, p)[0][0]
@@ -88,7 +90,7 @@ def replay(d, backends):
         n, len(p.primes), p.version[0], p.version[1], "confirmed" if hash_ok else "NOT reproduced (level taken from coeff_mod_count)"))
     failures = 0
     for be_cls in backends:
-        be = be_cls(p, rlk, gks)
+        be = be_cls(p, rlk, gks, rounding)
         prod = be.multiply(x.data, y.data)
         rel = be.relinearize(prod)
         res = be.rescale(rel)
@@ -146,6 +148,10 @@ def main():
     ap.add_argument("dir", nargs="?")
     ap.add_argument("--backend", default="both", choices=["cuda", "oracle", "both"])
     ap.add_argument("--self-test", action="store_true")
+    ap.add_argument("--rounding", default="auto", choices=["auto", "0", "1", "2", "3"],
+                    help="divide-by-last-prime convention (ckks_ctx_set_rounding): 1 = round in key switch and rescale (default), "
+                         "0 = floor in both, 2 = round in key switch only, 3 = round in rescale only; auto tries 1, then the others, "
+                         "and reports which convention reproduces the files")
     args = ap.parse_args()
     backends = {"cuda": [CudaBackend], "oracle": [OracleBackend], "both": [OracleBackend, CudaBackend]}[args.backend]
     if args.self_test:
@@ -155,7 +161,14 @@ def main():
     else:
         if not args.dir:
             ap.error("DIR (or --self-test) is required")
-        failures = replay(args.dir, backends)
+        modes = [1, 2, 3, 0] if args.rounding == "auto" else [int(args.rounding)]
+        for mode in modes:
+            print("---- rounding mode %d" % mode)
+            failures = replay(args.dir, backends, mode)
+            if failures == 0:
+                print("rounding mode %d reproduces the files%s" % (mode, "" if mode == 1 else
+                      " -- NOT the engine default: set ckks_ctx_set_rounding(ctx, %d) / flip the default" % mode))
+                break
     print("%d op(s) differ" % failures)
     sys.exit(1 if failures else 0)
 
