@@ -6,7 +6,7 @@ import re
 import sys
 
 
-def main(src, dst):
+def main(src, dst, tag="r02"):
     rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("==")) if len(r) > 5]
     hdr = rows[0]
     ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -20,11 +20,11 @@ def main(src, dst):
         cnt[name] += 1
     total = sum(tot.values())
     with open(dst, "w") as f:
-        f.write("# r01: ncu launch list of `bench.py --steps 1 --warmup 1 --ncu` (first %d launches of the timed epoch)\n\n" % sum(cnt.values()))
+        f.write("# %s: ncu launch list of `bench.py --steps 1 --warmup 1 --ncu` (first %d launches of the timed epoch)\n\n" % (tag, sum(cnt.values())))
         f.write("command: ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 3000 "
                 "python bench.py --steps 1 --warmup 1 --no-cpu --no-sweep --ncu\n")
         f.write("per-launch times are cold-cache and serialised (the two lanes and the FP64/integer inner-product kernels "
-                "overlap in a real run): compare SHARES.  Full list: r01_bench_launches.csv.gz\n\n")
+                "overlap in a real run): compare SHARES.  Full list: %s_bench_launches.csv.gz\n\n" % tag)
         f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
         for k, v in tot.most_common():
             f.write("| %s | %d | %.1f | %.1f%% |\n" % (k, cnt[k], v, 100 * v / total))
@@ -32,4 +32,4 @@ def main(src, dst):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(*sys.argv[1:4])
