@@ -667,6 +667,20 @@ def linear_transform_sharded(torch, eng, client, par, local, rank, world, timed,
                 "key_switches": int(plans.get(range(bd.b)).keyswitches + plans.get([g * bd.b for g in range(bd.G)]).keyswitches + 1),
                 "max_abs_err_vs_plain": float(np.abs(enc.decode(decr.decrypt(out_b))[0, :d] - U @ v).max()),
                 "note": "not the reference's op sequence; ciphertexts differ, decrypted result agrees"}
+    hoisted = None
+    if world == 1:   # SURVEY 8(f4) mode beside it: hoisted rotations (one digit decomposition shared by all d-1 rotations)
+        keys_h = kg.keyset(steps=[-d] + list(range(1, d)), relin=False)        # a Galois key for every step itself
+        plans_h = wl.PlanCache(ctx, keys_h)
+        ms_h, out_h, _, _, _ = timed(lambda: wl.linear_transform_plain_hoisted(ev, ct, diags, keys_h, plans_h), 3, 20)
+        bdh = wl.BsgsDiagonals(U, SCALE, enc, baby=16)
+        ms_bh, out_bh, _, _, _ = timed(lambda: wl.linear_transform_plain_bsgs_hoisted(ev, ct, bdh, keys_h, plans_h), 3, 20)
+        hoisted = {"ms": ms_h / 20, "key_switch_inner_products": d, "full_key_switches": 1, "galois_keys": d,
+                   "max_abs_err_vs_plain": float(np.abs(enc.decode(decr.decrypt(out_h))[0, :d] - U @ v).max()),
+                   "bsgs_hoisted_ms": ms_bh / 20,
+                   "bsgs_hoisted_max_abs_err_vs_plain": float(np.abs(enc.decode(decr.decrypt(out_bh))[0, :d] - U @ v).max()),
+                   "note": "not the reference's op sequence (SEAL permutes before lifting digits): ciphertexts differ, decrypted "
+                           "result agrees within key-switch noise; needs one Galois key per step instead of SEAL's default 2 log2 N"}
+        del keys_h, plans_h
     ms_eager, out, _, _, _ = timed(sharded, 3, 20)
     # the transform is ~40 short launches per GPU (<= 4 dependent NAF rounds) + one all-gather: at 8 GPUs the host launch
     # path, not the GPU, sets the pace.  Capture the whole sharded transform (rotation rounds, fused products, NCCL
@@ -690,7 +704,7 @@ def linear_transform_sharded(torch, eng, client, par, local, rank, world, timed,
     return {"workload": "Linear_Transform_Plain d=%d, N=%d, {60,40,40,60}, diagonals sharded over %d GPU(s)" % (d, 1 << log_n, world),
             "ms": ms / 20, "transforms_per_s": 20e3 / ms, "scaling": "strong", "key_switches_per_gpu": int(ks_local),
             "cuda_graph": graphed, "ms_eager_launches": ms_eager / 20, "rounds": int(plans.get(mine).rounds),
-            "bit_identical_to_unsharded": same, "max_abs_err_vs_plain": err, "bsgs_mode": bsgs}
+            "bit_identical_to_unsharded": same, "max_abs_err_vs_plain": err, "bsgs_mode": bsgs, "hoisted_mode": hoisted}
 
 
 def _primes():

@@ -174,6 +174,13 @@ int ckks_rotplan_rounds(const ckks_rotplan *plan);
 int ckks_rotate_plan(ckks_ctx *ctx, const ckks_rotplan *plan, const ckks_view *in, const ckks_view *out,
                      const ckks_view *scratch, ckks_stream s);
 
+/* SURVEY 8(f4), opt-in: every rotation of the plan applied to ONE ciphertext (in->batch == 1) with a SHARED digit
+ * decomposition ("hoisting", Halevi-Shoup): the hot loop of Linear_Transform_Plain / _Cipher (helper.h:252-257) rotates the same
+ * ct_new d-1 times.  Every non-zero step needs its own Galois key (KeyGenerator::galois_keys(steps); no NAF chains).  The
+ * result decrypts to the same values as ckks_rotate_plan within key-switch noise but its polynomials are NOT bit-identical
+ * to SEAL's (SEAL permutes before lifting the digits), so the reference-parity path never calls this. */
+int ckks_rotate_plan_hoisted(ckks_ctx *ctx, const ckks_rotplan *plan, const ckks_view *in, const ckks_view *out, ckks_stream s);
+
 /* The rotate-and-sum loop of cipher_dot_product (helper.h:472-476), `count` times:
  *     dup = rotate_vector(dup, steps);  acc = acc + dup
  * on a batch of independent ciphertexts.  `a` holds dup on entry; the rotation ping-pongs between

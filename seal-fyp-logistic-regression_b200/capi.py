@@ -83,6 +83,7 @@ SIGNATURES = {
     "ckks_rotplan_keyswitches": (C.c_uint64, [C.c_void_p]),
     "ckks_rotplan_rounds": (C.c_int, [C.c_void_p]),
     "ckks_rotate_plan": (C.c_int, [C.c_void_p, C.c_void_p, _VP, _VP, _VP, C.c_void_p]),
+    "ckks_rotate_plan_hoisted": (C.c_int, [C.c_void_p, C.c_void_p, _VP, _VP, C.c_void_p]),
     "ckks_rotate_sum_chain": (C.c_int, [C.c_void_p, C.c_void_p, _VP, _VP, _VP, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "ckks_multiply_plain_sum": (C.c_int, [C.c_void_p, _VP, _VP, _VP, C.c_void_p]),
     "ckks_multiply_sum": (C.c_int, [C.c_void_p, _VP, _VP, _VP, C.c_void_p]),

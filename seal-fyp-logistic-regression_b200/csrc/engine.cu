@@ -1097,6 +1097,80 @@ extern "C" int ckks_rotate_plan(ckks_ctx *c, const ckks_rotplan *p, const ckks_v
     return CKKS_OK;
 }
 
+// ------------------------------------------------------------------------------------ hoisted rotations
+// All rotations of a plan applied to ONE ciphertext with a shared digit decomposition (kernels.cuh, "hoisted rotations").
+// Every non-zero step of the plan must have its own Galois key (no NAF chains: a chained step acts on a different input).
+// NOT bit-identical to SEAL's rotate_vector (same decrypted values within key-switch noise): an explicit opt-in mode.
+extern "C" int ckks_rotate_plan_hoisted(ckks_ctx *c, const ckks_rotplan *p, const ckks_view *in, const ckks_view *out, ckks_stream s) {
+    int rc;
+    if (!p) return fail(CKKS_ERR_INVALID, "null plan");
+    if ((rc = check_view(c, in, "encrypted")) || (rc = check_view(c, out, "out"))) return rc;
+    if (in->size != 2 || out->size != 2) return fail(CKKS_ERR_INVALID, "encrypted size must be 2");
+    if (in->batch != 1) return fail(CKKS_ERR_INVALID, "hoisted rotations share the decomposition of ONE input ciphertext");
+    if (in->limbs > c->K - 1) return fail(CKKS_ERR_INVALID, "encrypted is not valid for encryption parameters");
+    if (out->batch != p->batch || out->limbs != in->limbs) return fail(CKKS_ERR_INVALID, "rotate_plan: batch/level mismatch");
+    if (out->data == in->data) return fail(CKKS_ERR_INVALID, "rotate_plan: out must not alias in");
+    if (p->round_cnt.size() > 1) return fail(CKKS_ERR_INVALID, "Galois key not present (hoisting needs a key for every step itself)");
+    CU(cudaSetDevice(c->device));
+    if ((rc = sync_key_tables(p->ks))) return rc;
+    cudaStream_t st = (cudaStream_t)s;
+    const int L = in->limbs, K = c->K;
+    const size_t N = c->n;
+    KsRoute rt{};
+    rt.v[0] = dv(in);
+    rt.v[0].bs = 0;
+    rt.v[1] = dv(out);
+    rt.v[2] = dv(out);
+    for (int b : p->zero_entries) {   // rotate by 0: the input unchanged
+        DView dst = rt.v[1];
+        dst.data += (u64)b * dst.bs;
+        k_ew_copy<<<ew_grid(c, 2 * L, 1), 256, 0, st>>>(rt.v[0], dst, L, c->n);
+        LAUNCH_CHECK(c);
+    }
+    if (p->round_cnt.empty()) return CKKS_OK;
+    const int R = p->round_cnt[0];
+    const size_t shared_words = N * ((size_t)L + (size_t)L * (L + 1));
+    const size_t per_rot = N * (2 * (size_t)(L + 1) + 2 * (size_t)L);
+    size_t fit = c->ws_cap > shared_words * 8 ? (c->ws_cap - shared_words * 8) / (per_rot * 8) : 1;
+    if (fit < 1) fit = 1;
+    if (fit > 16384) fit = 16384;
+    const int Bc = (int)(fit < (size_t)R ? fit : (size_t)R);
+    if ((rc = ensure_ws(c, (shared_words + per_rot * Bc) * 8))) return rc;
+    u64 *D = c->ws, *T1 = D + (size_t)L * N, *ACC = T1 + (size_t)L * (L + 1) * N, *T2 = ACC + (size_t)Bc * 2 * (L + 1) * N;
+    KsRoute r0 = rt;       // decomposition of the input: no permutation, no per-entry routing
+    r0.tgt_poly = 1;
+    rt.tgt_poly = 1;
+    rt.perm_tab = p->ks->d_perm_tab;
+    rt.key_tab = p->ks->d_key_tab;
+    rt.key_tiled = 1;
+#define RUN(LN)                                                                                                     \
+    {                                                                                                               \
+        typedef NttGeo<LN> G;                                                                                       \
+        k_ks_intt_row<LN, false><<<dim3(G::ROW_TILES, L, 1), NTT_THREADS, 0, st>>>(r0, D, L, c->t);                 \
+        LAUNCH_CHECK(c);                                                                                            \
+        k_ks_invcol_modup<LN><<<dim3(G::COL_TILES, L, 1), NTT_THREADS, 0, st>>>(D, T1, L, 1, c->t);                 \
+        LAUNCH_CHECK(c);                                                                                            \
+        k_hoist_finish<LN><<<dim3(G::ROW_TILES, L *(L + 1), 1), NTT_THREADS, 0, st>>>(T1, rt.v[0], L, c->t);        \
+        LAUNCH_CHECK(c);                                                                                            \
+        for (int b0 = 0; b0 < R; b0 += Bc) {                                                                        \
+            const int bc = (R - b0) < Bc ? (R - b0) : Bc;                                                           \
+            rt.sel = p->d_sel + p->round_off[0];                                                                    \
+            rt.b0 = b0;                                                                                             \
+            DView spec{ACC + (size_t)L * N, (u64)(L + 1) * N, 0};                                                   \
+            DView minu{ACC, 2 * (u64)(L + 1) * N, (u64)(L + 1) * N};                                                \
+            k_hoist_mac<LN><<<dim3(G::ROW_TILES, L + 1, bc), NTT_THREADS, 0, st>>>(T1, rt, ACC, L, c->t);           \
+            LAUNCH_CHECK(c);                                                                                        \
+            k_md_invcol_fwdcol<LN><<<dim3(G::COL_TILES, 1, 2 * bc), NTT_THREADS, 0, st>>>(spec, T2, L, K - 1, 1, c->t); \
+            LAUNCH_CHECK(c);                                                                                        \
+            k_md_fwd_row<LN, 2><<<dim3(G::ROW_TILES, L, 2 * bc), NTT_THREADS, 0, st>>>(T2, minu, rt, 2, L, K - 1, c->t); \
+            LAUNCH_CHECK(c);                                                                                        \
+        }                                                                                                           \
+    }
+    DISPATCH_LOGN(c, RUN)
+#undef RUN
+    return CKKS_OK;
+}
+
 // ------------------------------------------------------------------------------------ fused products
 static int mul_sum(ckks_ctx *c, bool plain, const ckks_view *a, const ckks_view *b, const ckks_view *o, cudaStream_t st) {
     int rc;

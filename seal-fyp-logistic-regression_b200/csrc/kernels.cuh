@@ -827,6 +827,148 @@ __global__ void __launch_bounds__(NTT_THREADS, V_MDROW_OCC) k_md_fwd_row(const u
     }
 }
 
+// =============================================================================== hoisted rotations
+// Many rotations of ONE ciphertext (the hot loop of Linear_Transform_*, helper.h:252-257: every rotation acts on the same
+// ct_new) can share the digit decomposition: decompose c1 once (digit INTT + mod-up NTT into every prime), then per rotation
+// only permute the extended digits (the Galois automorphism is a permutation in NTT form), take the inner product with
+// that rotation's key and mod-down.  SEAL permutes BEFORE it lifts the digits to non-negative residues, so the hoisted
+// digits differ from SEAL's by multiples of q_i on the negated coefficients: the result decrypts to the same values within
+// key-switch noise but is NOT bit-identical -- a separate, tolerance-checked mode, never the default.
+//
+// (h1) finish the mod-up transform: T1[i][jj] holds the column pass (k_ks_invcol_modup); run the row pass and store the
+// canonical NTT values in place; the slot of the digit's own prime receives the NTT-form limb of c1 itself.
+template <int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_hoist_finish(u64 *T1, DView ct, int L, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int i = blockIdx.y / (L + 1), jj = blockIdx.y % (L + 1);
+    const int pj = jj == L ? t.K - 1 : jj;
+    u64 *tile = T1 + ((u64)i * (L + 1) + jj) * G::N + (u64)blockIdx.x * NTT_TILE;
+    const int t0 = blockIdx.x * NTT_TILE;
+    u64 x[8];
+    if (pj == i) {
+        load8(x, ct.data + ct.ps + (u64)i * G::N + t0 + 8 * threadIdx.x);   // poly 1, limb i
+        store8(tile + 8 * threadIdx.x, x);
+        return;
+    }
+    const ModConst m = load_mod(t, pj);
+    const FpConst f = t.fp[pj];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = tile[row_strided_li<LOGN>(e)];
+    if (f.ok != 0.0) {
+        double xd[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) xd[e] = bits_fp(x[e]);
+        fwd_row_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, t0, as_fp(smem));
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = fp_to_canonical(xd[e], f);
+    } else {
+        fwd_row_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, t0, smem);
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = reduce64(x[e], m);
+    }
+    __syncthreads();   // every thread has read its inputs long ago; the outputs overwrite the same tile
+    store8(tile + 8 * threadIdx.x, x);
+}
+
+// (h2) per rotation z: acc_k[jj][g] = sum_i T1F[i][jj][perm_z[g]] * ksk_z[i][k][jj][g]; the special-prime limb continues
+// into the mod-down INTT's row pass like k_ks_mac.  grid (ROW_TILES, L + 1, rotations).
+template <int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS, 2) k_hoist_mac(const u64 *T1F, KsRoute rt, u64 *ACC, int L, Tables t) {
+    typedef NttGeo<LOGN> G;
+    __shared__ u64 smem[NTT_TILE];
+    const int jj = L - (int)blockIdx.y, b = blockIdx.z;   // special-prime limb first
+    const KsSel sl = route_sel(rt, b);
+    const uint32_t *__restrict__ perm = route_perm(rt, sl);
+    const u64 *__restrict__ ksk = route_key(rt, sl);
+    const int K = t.K, pj = jj == L ? K - 1 : jj;
+    const ModConst m = load_mod(t, pj);
+    const FpConst f = t.fp[pj];
+    const int t0 = blockIdx.x * NTT_TILE;
+    unsigned ix[8];
+    load_perm8(ix, perm + t0 + 8 * threadIdx.x);
+    const int koff = rt.key_tiled ? 2 * threadIdx.x : 8 * threadIdx.x, kstep = rt.key_tiled ? 256 : 1;
+    u64 *o0 = ACC + (((u64)b * 2 + 0) * (L + 1) + jj) * G::N + t0;
+    u64 *o1 = ACC + (((u64)b * 2 + 1) * (L + 1) + jj) * G::N + t0;
+    u64 r0[8], r1[8];
+    if (f.ok != 0.0) {
+        double a0[8], a1[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) a0[e] = a1[e] = 0.0;
+        for (int i = 0; i < L; i++) {
+            const u64 *src = T1F + ((u64)i * (L + 1) + jj) * G::N;
+            const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + koff);
+            const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + koff);
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const ulonglong2 a = __ldg(k0 + kstep * v), c = __ldg(k1 + kstep * v);
+                const double x0 = fp_from_u64(src[ix[2 * v]]), x1 = fp_from_u64(src[ix[2 * v + 1]]);
+                const double kax = rt.key_tiled ? bits_fp(a.x) : fp_from_u64(a.x), kay = rt.key_tiled ? bits_fp(a.y) : fp_from_u64(a.y);
+                const double kcx = rt.key_tiled ? bits_fp(c.x) : fp_from_u64(c.x), kcy = rt.key_tiled ? bits_fp(c.y) : fp_from_u64(c.y);
+                a0[2 * v] = __dadd_rn(a0[2 * v], fp_mulmod(x0, kax, f));
+                a0[2 * v + 1] = __dadd_rn(a0[2 * v + 1], fp_mulmod(x1, kay, f));
+                a1[2 * v] = __dadd_rn(a1[2 * v], fp_mulmod(x0, kcx, f));
+                a1[2 * v + 1] = __dadd_rn(a1[2 * v + 1], fp_mulmod(x1, kcy, f));
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            r0[e] = fp_to_canonical(a0[e], f);
+            r1[e] = fp_to_canonical(a1[e], f);
+        }
+    } else {
+        u64 lo0[8], hi0[8], lo1[8], hi1[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) lo0[e] = hi0[e] = lo1[e] = hi1[e] = 0;
+        for (int i = 0; i < L; i++) {
+            const u64 *src = T1F + ((u64)i * (L + 1) + jj) * G::N;
+            const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + koff);
+            const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + koff);
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const ulonglong2 a = __ldg(k0 + kstep * v), c = __ldg(k1 + kstep * v);
+                const u64 x0 = src[ix[2 * v]], x1 = src[ix[2 * v + 1]];
+                mac128(lo0[2 * v], hi0[2 * v], x0, a.x);
+                mac128(lo0[2 * v + 1], hi0[2 * v + 1], x1, a.y);
+                mac128(lo1[2 * v], hi1[2 * v], x0, c.x);
+                mac128(lo1[2 * v + 1], hi1[2 * v + 1], x1, c.y);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            r0[e] = barrett128(lo0[e], hi0[e], m);
+            r1[e] = barrett128(lo1[e], hi1[e], m);
+        }
+    }
+    if (jj == L) {   // special-prime limb: mod-down INTT row pass fused (its column pass follows in k_md_invcol_fwdcol)
+        if (f.ok != 0.0) {
+            double xd[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(r0[e]);
+            inv_row_pass_fp<LOGN>(xd, t.twid + (size_t)pj * G::N, f, t0, as_fp(smem));
+#pragma unroll
+            for (int e = 0; e < 8; e++) o0[row_strided_li<LOGN>(e)] = fp_bits(xd[e]);
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(r1[e]);
+            inv_row_pass_fp<LOGN>(xd, t.twid + (size_t)pj * G::N, f, t0, as_fp(smem));
+#pragma unroll
+            for (int e = 0; e < 8; e++) o1[row_strided_li<LOGN>(e)] = fp_bits(xd[e]);
+        } else {
+            inv_row_pass<LOGN>(r0, t.twi + (size_t)pj * G::N, m, t0, smem);
+#pragma unroll
+            for (int e = 0; e < 8; e++) o0[row_strided_li<LOGN>(e)] = r0[e];
+            __syncthreads();
+            inv_row_pass<LOGN>(r1, t.twi + (size_t)pj * G::N, m, t0, smem);
+#pragma unroll
+            for (int e = 0; e < 8; e++) o1[row_strided_li<LOGN>(e)] = r1[e];
+        }
+        return;
+    }
+    store8(o0 + 8 * threadIdx.x, r0);
+    store8(o1 + 8 * threadIdx.x, r1);
+}
+
 // Key-switch keys are static: at registration the engine makes a private copy in which, inside every 2048-word
 // tile, word pair v (0..3) of thread t (0..255) is stored at 512 v + 2 t instead of 8 t + 2 v, so that the
 // inner-product kernels' 16-byte key loads are contiguous across a warp.

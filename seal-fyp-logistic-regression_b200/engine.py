@@ -458,6 +458,21 @@ class Evaluator:
         out.scale = ct.scale
         return out
 
+    def rotate_plan_hoisted(self, ct, plan, out=None):
+        """SURVEY 8(f4), opt-in: all rotations of `plan` applied to the single ciphertext `ct` with one shared digit
+        decomposition.  Needs a Galois key for every step itself; same decrypted values as rotate_plan within
+        key-switch noise, NOT bit-identical polynomials."""
+        if ct.batch != 1:
+            raise capi.CkksInvalidArgument("hoisted rotations act on one ciphertext")
+        if out is None:
+            out = Ciphertext(self.ctx, torch.empty((plan.batch, 2, ct.cap, self.ctx.n), dtype=torch.int64,
+                                                   device=ct.data.device), ct.limbs, ct.scale)
+        out.limbs = ct.limbs
+        vi, vo = ct.view(), out.view()
+        check(self.lib.ckks_rotate_plan_hoisted(self.h, plan._h, C.byref(vi), C.byref(vo), _stream()))
+        out.scale = ct.scale
+        return out
+
     def rotate_sum_chain(self, dup, acc, steps, count, keys, scratch=None):
         """`count` times: dup = rotate_vector(dup, steps); acc += dup (fused, CUDA-graph replayed).
         Returns the Ciphertext that holds dup afterwards (dup's or scratch's storage)."""

@@ -372,3 +372,63 @@ def test_sparse_diagonal_sets_match_dense(make_fixture):
     assert np.array_equal(got.numpy(), want.numpy())
     dec = fx.orc.decode(fx.orc.decrypt(fx.sk, got.numpy()[0]), got.scale)[: d * d].reshape(d, d)
     assert np.abs(dec - A @ B).max() < 1e-3
+
+
+def test_hoisted_rotations_mode(make_fixture):
+    """rotations of ONE ciphertext with a shared digit decomposition (ckks_rotate_plan_hoisted).  Not the
+    reference's polynomials (SEAL permutes before lifting digits) -- checked the way north_star checks decrypted outputs:
+    every hoisted rotation decrypts to the same slots as SEAL-order rotate_vector within key-switch noise (2^-19 at scale 2^40), on
+    both arithmetic paths (integer limbs and FP64 limbs), at the top level and one level down, and the hoisted
+    Linear_Transform_Plain / BSGS variants equal U @ v."""
+    wl, _, client = _mods()
+    steps = [-16] + list(range(1, 16)) + [16, 32, 48]
+    fx = make_fixture(13, [60, 40, 40, 60], steps=tuple(steps))
+    plans = wl.PlanCache(fx.ctx, fx.keys)
+    enc = client.CKKSEncoder(fx.ctx)
+    rng = np.random.default_rng(40)
+    scale = 2.0 ** 40
+    x = rng.uniform(-1, 1, 64)
+    full = np.zeros(fx.n // 2)
+    full[:64] = x
+    for L in (fx.L, fx.L - 1):
+        ct = fx.ctx.upload(_enc(fx, 700 + L, x, scale)[:, :L], cap=fx.L, scale=scale)
+        plan = plans.get([0, 1, 2, 3, 5, 7, 11, 15, -16])
+        ref = fx.ev.rotate_plan(ct, plan)
+        got = fx.ev.rotate_plan_hoisted(ct, plan)
+        assert got.limbs == L and got.batch == plan.batch
+        assert np.array_equal(got.numpy()[0], ct.numpy()[0])                     # rotate by 0 = the input
+        assert not np.array_equal(got.numpy()[1:], ref.numpy()[1:])              # different polynomials ...
+        for b, st in enumerate(plan.steps):                                     # ... same plaintext
+            dg = fx.orc.decode(fx.orc.decrypt(fx.sk, got.numpy()[b]), scale)
+            dr = fx.orc.decode(fx.orc.decrypt(fx.sk, ref.numpy()[b]), scale)
+            # key-switch noise at N = 8192 with one 60-bit special prime is ~1e-6 on slots of magnitude 1 (the SEAL-order
+            # rotation shows the same): bound 2^-19 against the exact rotation, 2^-18 between the two noisy results
+            assert np.abs(dg - np.roll(full, -st)).max() < 2.0 ** -19, (L, st)
+            assert np.abs(dr - np.roll(full, -st)).max() < 2.0 ** -19, (L, st)
+            assert np.abs(dg - dr).max() < 2.0 ** -18, (L, st)
+    # a step without its own key cannot be hoisted (it would be a NAF chain)
+    capi = importlib.import_module(PKG + ".capi")
+    ct = fx.ctx.upload(_enc(fx, 710, x, scale), scale=scale)
+    with pytest.raises(capi.CkksInvalidArgument, match="key"):
+        fx.ev.rotate_plan_hoisted(ct, plans.get([1, 17]))
+    # Linear_Transform_Plain, hoisted and BSGS + hoisted baby steps
+    d = 16
+    U, v = rng.uniform(0, 1, (d, d)), rng.uniform(0, 1, d)
+    ctv = fx.ctx.upload(_enc(fx, 720, v, scale), scale=scale)
+    diags = enc.encode(wl.all_diagonals(U), scale)
+    ref = wl.linear_transform_plain(fx.ev, ctv, diags, fx.keys, plans)
+    got = wl.linear_transform_plain_hoisted(fx.ev, ctv, diags, fx.keys, plans)
+    assert got.limbs == ref.limbs and got.scale == ref.scale and not np.array_equal(got.numpy(), ref.numpy())
+    dg = fx.orc.decode(fx.orc.decrypt(fx.sk, got.numpy()[0]), got.scale)[:d]
+    dr = fx.orc.decode(fx.orc.decrypt(fx.sk, ref.numpy()[0]), ref.scale)[:d]
+    assert np.abs(dg - dr).max() < 1e-5 and np.abs(dg - U @ v).max() < 1e-4
+    d = 64
+    U, v = rng.uniform(0, 1, (d, d)), rng.uniform(0, 1, d)
+    fx2 = make_fixture(13, [60, 40, 40, 60], steps=tuple([-64] + list(range(1, 16)) + [16, 32, 48]))
+    plans2 = wl.PlanCache(fx2.ctx, fx2.keys)
+    enc2 = client.CKKSEncoder(fx2.ctx)
+    ctv = fx2.ctx.upload(_enc(fx2, 721, v, scale), scale=scale)
+    bd = wl.BsgsDiagonals(U, scale, enc2, baby=16)
+    got = wl.linear_transform_plain_bsgs_hoisted(fx2.ev, ctv, bd, fx2.keys, plans2)
+    dg = fx2.orc.decode(fx2.orc.decrypt(fx2.sk, got.numpy()[0]), got.scale)[:d]
+    assert np.abs(dg - U @ v).max() < 1e-4
