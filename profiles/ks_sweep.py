@@ -81,7 +81,9 @@ def run(log_n, top, cases):
     del ctx
 
 
-if quick:
+if "--small" in sys.argv:      # the per-GPU batches of the strong-scaling run (32 chains over 2 / 4 / 8 GPUs) and below
+    run(15, 9, [(3, 16, 30), (3, 8, 30), (3, 4, 30), (3, 2, 30)])
+elif quick:
     run(15, 9, [(3, 32, 20), (3, 4, 20), (9, 32, 10)])
 else:
     run(15, 9, [(3, 32, 30), (3, 16, 30), (3, 8, 30), (3, 4, 30), (3, 1, 30), (9, 32, 10), (9, 4, 10)])

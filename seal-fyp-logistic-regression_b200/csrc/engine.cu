@@ -893,52 +893,76 @@ extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const c
             CU(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
         }
-        cudaGraphExec_t execs[4] = {nullptr, nullptr, nullptr, nullptr};
-        uint64_t per_pair = 0;
-        for (int li = 0; li < nl; li++) {
-            const int off = split[li], cnt = split[li + 1] - split[li];
-            if ((rc = ensure_lane(c, li, ks_words_per_ct(c, L) * 8 * (size_t)ks_chunk(c, cnt, L)))) return rc;
-            ckks_ctx::Lane &ln = c->lane[li];
-            int key_tiled = 0;
-            std::vector<uint64_t> key = {(uint64_t)a->data, (uint64_t)b->data, (uint64_t)acc->data, (uint64_t)resolve_key(c, it->second, &key_tiled), g,
-                                         (uint64_t)L, (uint64_t)off, (uint64_t)cnt, a->batch_stride, a->poly_stride, b->batch_stride,
-                                         b->poly_stride, acc->batch_stride, acc->poly_stride, (uint64_t)ln.ws, (uint64_t)c->t.round_half};
-            auto gi = c->chain_graphs.find(key);
-            if (gi == c->chain_graphs.end()) {
-                cudaGraph_t graph = nullptr;
-                uint64_t before = c->launches;
-                CU(cudaStreamBeginCapture(ln.main, cudaStreamCaptureModeThreadLocal));
-                rc = one(a, b, ln.main, false, li, off, cnt);
-                if (!rc) rc = one(b, a, ln.main, true, li, off, cnt);
-                cudaError_t ce = cudaStreamEndCapture(ln.main, &graph);
-                uint64_t per = c->launches - before;
-                c->launches = before;
-                if (rc) return rc;
-                if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
-                ckks_ctx::ChainGraph cg{};
-                cg.launches = per;
-                ce = cudaGraphInstantiate(&cg.exec, graph, 0);
-                cudaGraphDestroy(graph);
-                if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
-                if (c->chain_graphs.size() > 64) {   // bounded cache
-                    for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
-                    c->chain_graphs.clear();
+        // graphs of 1 and of CHAIN_GRAPH_PAIRS ping-pong pairs per lane: a long chain replays the big one (one graph launch
+        // per 2 * CHAIN_GRAPH_PAIRS dependent steps -- fewer launch gaps between graphs, less host work), the remainder
+        // the small one
+        const int pairs = count / 2;
+        static const int big_pairs = getenv("CKKS_CHAIN_GRAPH_PAIRS") ? atoi(getenv("CKKS_CHAIN_GRAPH_PAIRS")) : 8;
+        cudaGraphExec_t execs[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+        uint64_t per_graph[2] = {0, 0};
+        const int gp[2] = {1, big_pairs > 1 && pairs >= big_pairs ? big_pairs : 0};
+        for (int which = 0; which < 2; which++) {
+            if (!gp[which]) continue;
+            for (int li = 0; li < nl; li++) {
+                const int off = split[li], cnt = split[li + 1] - split[li];
+                if ((rc = ensure_lane(c, li, ks_words_per_ct(c, L) * 8 * (size_t)ks_chunk(c, cnt, L)))) return rc;
+                ckks_ctx::Lane &ln = c->lane[li];
+                int key_tiled = 0;
+                std::vector<uint64_t> key = {(uint64_t)a->data, (uint64_t)b->data, (uint64_t)acc->data, (uint64_t)resolve_key(c, it->second, &key_tiled), g,
+                                             (uint64_t)L, (uint64_t)off, (uint64_t)cnt, a->batch_stride, a->poly_stride, b->batch_stride,
+                                             b->poly_stride, acc->batch_stride, acc->poly_stride, (uint64_t)ln.ws, (uint64_t)c->t.round_half,
+                                             (uint64_t)gp[which]};
+                auto gi = c->chain_graphs.find(key);
+                if (gi == c->chain_graphs.end()) {
+                    cudaGraph_t graph = nullptr;
+                    uint64_t before = c->launches;
+                    CU(cudaStreamBeginCapture(ln.main, cudaStreamCaptureModeThreadLocal));
+                    for (int q = 0; q < gp[which] && !rc; q++) {
+                        rc = one(a, b, ln.main, q > 0, li, off, cnt);
+                        if (!rc) rc = one(b, a, ln.main, true, li, off, cnt);
+                    }
+                    cudaError_t ce = cudaStreamEndCapture(ln.main, &graph);
+                    uint64_t per = c->launches - before;
+                    c->launches = before;
+                    if (rc) return rc;
+                    if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+                    ckks_ctx::ChainGraph cg{};
+                    cg.launches = per;
+                    ce = cudaGraphInstantiate(&cg.exec, graph, 0);
+                    cudaGraphDestroy(graph);
+                    if (ce != cudaSuccess) return fail(CKKS_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+                    if (c->chain_graphs.size() > 64) {   // bounded cache (graphs of this call are re-created on demand)
+                        for (auto &kv : c->chain_graphs) cudaGraphExecDestroy(kv.second.exec);
+                        c->chain_graphs.clear();
+                        for (auto &row : execs)
+                            for (auto &e : row) e = nullptr;
+                        which = -1;                   // start over: earlier handles of this call were just destroyed
+                        per_graph[0] = per_graph[1] = 0;
+                        cudaGraphExecDestroy(cg.exec);
+                        break;
+                    }
+                    gi = c->chain_graphs.emplace(key, cg).first;
                 }
-                gi = c->chain_graphs.emplace(key, cg).first;
+                execs[which][li] = gi->second.exec;
+                per_graph[which] += gi->second.launches;
             }
-            execs[li] = gi->second.exec;
-            per_pair += gi->second.launches;
         }
         CU(cudaEventRecord(c->ev_in, user));
-        const int pairs = count / 2;
         for (int li = 0; li < nl; li++) CU(cudaStreamWaitEvent(c->lane[li].main, c->ev_in, 0));
-        for (int i = 0; i < pairs; i++)
-            for (int li = 0; li < nl; li++) CU(cudaGraphLaunch(execs[li], c->lane[li].main));
+        int left = pairs;
+        if (gp[1])
+            for (; left >= gp[1]; left -= gp[1]) {
+                for (int li = 0; li < nl; li++) CU(cudaGraphLaunch(execs[1][li], c->lane[li].main));
+                c->launches += per_graph[1];
+            }
+        for (; left > 0; left--) {
+            for (int li = 0; li < nl; li++) CU(cudaGraphLaunch(execs[0][li], c->lane[li].main));
+            c->launches += per_graph[0];
+        }
         for (int li = 0; li < nl; li++) {
             CU(cudaEventRecord(c->lane[li].end, c->lane[li].main));
             CU(cudaStreamWaitEvent(user, c->lane[li].end, 0));
         }
-        c->launches += per_pair * (uint64_t)pairs;
         done = pairs * 2;
     }
     const ckks_view *src = a, *dst = b;

@@ -267,9 +267,10 @@ def test_full_size_properties_n32768(make_fixture):
                 assert np.abs(c).max() < 2 ** 24, (step, i, j)
 
 
-@pytest.mark.parametrize("batch,count", [(1, 1), (3, 4), (5, 9), (16, 6), (19, 7), (33, 12)])
+@pytest.mark.parametrize("batch,count", [(1, 1), (3, 4), (5, 9), (16, 6), (19, 7), (33, 12), (2, 19), (17, 35)])
 def test_rotate_sum_chain_matches_sequential(make_fixture, batch, count):
-    """ckks_rotate_sum_chain (fused add, CUDA-graph replay, two concurrent lanes for batches >= 16)
+    """ckks_rotate_sum_chain (fused add, CUDA-graph replay -- graphs of 8 ping-pong pairs for long chains, of 1 pair and
+    single eager steps for the remainder --, two concurrent lanes for batches >= 16)
     equals `count` sequential rotate_vector + add_inplace steps of the oracle (helper.h:472-476)"""
     fx = make_fixture(12, CHAINS[12])
     rng = np.random.default_rng(100 + batch)
