@@ -43,6 +43,9 @@ static int fail(int code, const std::string &msg) {
 // previous one drains; it runs its prologue (constants, first twiddles) and blocks at
 // griddepcontrol.wait until the predecessor's memory is visible.  Hides launch ramp-up between the
 // eight kernels of a key switch.
+// -1 = automatic (on for launches that carry >= 8 ciphertexts), 0 = never, 1 = always (CKKS_PDL)
+static int g_pdl_mode = getenv("CKKS_PDL") ? atoi(getenv("CKKS_PDL")) : -1;
+static thread_local bool g_pdl_now = false;   // decided per batched key switch (keyswitch()), read by launch_pdl
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
@@ -54,10 +57,9 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    // programmatic dependent launch paid off for the 9-launch pipeline of round 1; with the fused 5/6-launch pipeline it is
-    // neutral at large batches and costs 20 % at small ones (profiles/r02_keyswitch_experiments.md): off unless CKKS_PDL=1
-    static const bool use_pdl = getenv("CKKS_PDL") != nullptr && atoi(getenv("CKKS_PDL")) != 0;
-    cfg.numAttrs = use_pdl ? 1 : 0;
+    // Measured on the fused pipeline with the late trigger (N = 32768, L = 3): -6 % at batch 16, -5 % at 8, -2 % at 32 and at 2,
+    // but +7 % at batch 4 -- hence on from 8 ciphertexts per launch.
+    cfg.numAttrs = g_pdl_now ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -582,6 +584,7 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
     const bool special_small = (c->primes[K - 1] >> 41) == 0;
     for (int b0 = slot0; b0 < slot0 + nslots; b0 += Bc) {
         const int bc = (slot0 + nslots - b0) < Bc ? (slot0 + nslots - b0) : Bc;
+        g_pdl_now = g_pdl_mode < 0 ? bc >= 8 : g_pdl_mode != 0;
         rt.b0 = b0;
         DView dD{D, (u64)L * N, 0};
         DView spec{ACC + (size_t)L * N, (u64)(L + 1) * N, 0};             // special-prime limb of every (b,k)
@@ -1241,6 +1244,7 @@ extern "C" int ckks_rescale(ckks_ctx *c, const ckks_view *in, const ckks_view *o
     tr.round_half = c->round_rescale;
     for (int b0 = 0; b0 < B; b0 += Bc) {
         const int bc = (B - b0) < Bc ? (B - b0) : Bc;
+        g_pdl_now = g_pdl_mode < 0 ? bc * S >= 16 : g_pdl_mode != 0;
         DView src{(u64 *)in->data + (u64)b0 * in->batch_stride, in->batch_stride, in->poly_stride};
         DView last{src.data + (size_t)Lo * N, src.bs, src.ps};
         DView dR{R, (u64)S * N, (u64)N};

@@ -64,6 +64,11 @@ __device__ __forceinline__ void load_perm8(unsigned (&ix)[8], const uint32_t *pe
 // predecessor's results
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// A pipeline kernel lets its successor start (programmatic dependent launch) only once its own inputs are in registers
+// and its main work is under way -- PDL_LATE() sits after the loads / the first transform, before the final stores -- so
+// that just the immediate successor gets a head start for its prologue (round 1 triggered at the top of every kernel,
+// which cascades the whole pipeline into residency: slower at small batches, profiles/r02_keyswitch_experiments.md).
+#define PDL_LATE() pdl_launch_dependents()
 // ---- TMA 1-D bulk copy global -> shared with mbarrier completion (SASS: UBLKCP), used to stage the
 // next digit's 16 KB tile while the current digit is transformed
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -187,7 +192,6 @@ template <int LOGN>
 __global__ void __launch_bounds__(NTT_THREADS, 5) k_inv_row(DView src, DView dst, int limbs, int first_prime, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
-    pdl_launch_dependents();
     const int s = blockIdx.y / limbs, l = blockIdx.y % limbs, pj = first_prime + l;
     const u64 *in = src.data + blockIdx.z * src.bs + s * src.ps + (u64)l * G::N;
     u64 *out = dst.data + blockIdx.z * dst.bs + s * dst.ps + (u64)l * G::N;
@@ -217,7 +221,6 @@ template <int LOGN, bool ADD_HALF>
 __global__ void __launch_bounds__(NTT_THREADS) k_inv_col(DView src, DView dst, int limbs, int first_prime, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
-    pdl_launch_dependents();
     const int s = blockIdx.y / limbs, l = blockIdx.y % limbs, pj = first_prime + l;
     const u64 *in = src.data + blockIdx.z * src.bs + s * src.ps + (u64)l * G::N;
     u64 *out = dst.data + blockIdx.z * dst.bs + s * dst.ps + (u64)l * G::N;
@@ -260,7 +263,6 @@ template <int LOGN, bool GALOIS>
 __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_intt_row(KsRoute rt, u64 *D, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
-    pdl_launch_dependents();
     const int i = blockIdx.y, b = blockIdx.z;
     const KsSel sl = route_sel(rt, b);
     const DView tgt = rt.v[sl.src];
@@ -281,6 +283,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_intt_row(KsRoute rt, u64 
         load8(x, in + t0 + 8 * threadIdx.x);
     }
     const FpConst f = t.fp[i];
+    PDL_LATE();   // (inputs are in registers)
     if (f.ok != 0.0) {
         double xd[8];
 #pragma unroll
@@ -301,7 +304,6 @@ template <int LOGN>
 __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *D, u64 *T1, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
-    pdl_launch_dependents();
     const int i = blockIdx.y / (L + 1), jj = blockIdx.y % (L + 1), b = blockIdx.z;
     const int pj = jj == L ? t.K - 1 : jj;
     if (pj == i) return;  // that limb is taken directly from the NTT-form target
@@ -343,7 +345,6 @@ template <int LOGN>
 __global__ void __launch_bounds__(NTT_THREADS, 4) k_ks_invcol_modup(const u64 *D, u64 *T1, int L, int nsplit, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[2][NTT_TILE];   // alternating exchange buffers: no barrier needed between passes
-    pdl_launch_dependents();
     const int i = blockIdx.y / nsplit, part = blockIdx.y % nsplit, b = blockIdx.z;
     const u64 *in = D + ((u64)b * L + i) * G::N;
     const ModConst mi = load_mod(t, i);
@@ -365,6 +366,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_ks_invcol_modup(const u64 *D
 #pragma unroll
         for (int e = 0; e < 8; e++) v[e] = csub(csub(v[e], mi.p2), mi.p);
     }
+    PDL_LATE();
     int buf = 1, cnt = 0;
     for (int jj = 0; jj <= L; jj++) {
         const int pj = jj == L ? t.K - 1 : jj;
@@ -410,7 +412,6 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
     // TMA-staged input tiles of the current / next digit; the current one doubles as the exchange buffer
     __shared__ __align__(128) u64 stage[2][NTT_TILE];
     __shared__ u64 bars[2];
-    pdl_launch_dependents();
     const int jj = list.jj[blockIdx.y], b = blockIdx.z;
     const KsSel sl = route_sel(rt, b);
     const DView tgt = rt.v[sl.src];
@@ -479,6 +480,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
             mac128(lo1[2 * v + 1], hi1[2 * v + 1], x[2 * v + 1], c.y);
         }
     }
+    PDL_LATE();
     if (fuse_inv && jj == L) {
         // special-prime limb: the accumulated tile is exactly the input tile of the mod-down INTT's row pass --
         // run it here (k_inv_row fused), writing the strided-side result over the limb's slot in ACC
@@ -523,7 +525,6 @@ __global__ void __launch_bounds__(NTT_THREADS, V_MACFP_OCC) k_ks_mac_fp(const u6
     typedef NttGeo<LOGN> G;
     __shared__ __align__(128) u64 stage[2][NTT_TILE];   // TMA-staged tiles; the current one is also the exchange buffer
     __shared__ u64 bars[2];
-    pdl_launch_dependents();
     const int jj = list.jj[blockIdx.y], b = blockIdx.z;
     const KsSel sl = route_sel(rt, b);
     const DView tgt = rt.v[sl.src];
@@ -616,6 +617,7 @@ __global__ void __launch_bounds__(NTT_THREADS, V_MACFP_OCC) k_ks_mac_fp(const u6
             a1[2 * v + 1] = __dadd_rn(a1[2 * v + 1], fp_mulmod(x[2 * v + 1], kcy, f));
         }
     }
+    PDL_LATE();
     if (fuse_inv && jj == L) {   // small special prime: mod-down INTT row pass fused, as in k_ks_mac
         u64 *b0 = ACC + (((u64)b * 2 + 0) * (L + 1) + jj) * G::N + t0;
         u64 *b1 = ACC + (((u64)b * 2 + 1) * (L + 1) + jj) * G::N + t0;
@@ -650,7 +652,6 @@ template <int LOGN>
 __global__ void __launch_bounds__(NTT_THREADS, 5) k_md_fwd_col(DView R, u64 *T2, int Lout, int a, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
-    pdl_launch_dependents();
     const int j = blockIdx.y, z = blockIdx.z;
     const u64 *in = R.data + z * R.bs;
     u64 *out = T2 + ((u64)z * Lout + j) * G::N;
@@ -688,7 +689,6 @@ template <int LOGN>
 __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_invcol_fwdcol(DView R, u64 *T2, int Lout, int a, int nsplit, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[2][NTT_TILE];
-    pdl_launch_dependents();
     const int part = blockIdx.y, z = blockIdx.z;
     const u64 *in = R.data + z * R.bs;
     const ModConst ma = load_mod(t, a);
@@ -711,6 +711,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_md_invcol_fwdcol(DView R, u6
 #pragma unroll
         for (int e = 0; e < 8; e++) v[e] = csub(csub(csub(v[e], ma.p2), ma.p) + half, ma.p);
     }
+    PDL_LATE();
     int buf = 1;
     for (int j = part; j < Lout; j += nsplit) {
         const ModConst m = load_mod(t, j);
@@ -749,7 +750,6 @@ template <int LOGN, int MODE>
 __global__ void __launch_bounds__(NTT_THREADS, V_MDROW_OCC) k_md_fwd_row(const u64 *T2, DView minuend, KsRoute rt, int S, int Lout, int a, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
-    pdl_launch_dependents();
     const int j = blockIdx.y, z = blockIdx.z, b = z / S, s = z % S;
     const KsSel sl = route_sel(rt, b);
     const DView base = rt.v[sl.src], dst = rt.v[sl.dst];
@@ -794,6 +794,7 @@ __global__ void __launch_bounds__(NTT_THREADS, V_MDROW_OCC) k_md_fwd_row(const u
             for (int e = 0; e < 8; e++) bv[e] = bp[ix[e]];
         }
     }
+    PDL_LATE();
     // (minuend - NTT(u)) * q_a^-1 without canonicalising the transform output first: the lazy value
     // (< 8p + 2^32) is subtracted from minuend + 9p (a multiple of p, no underflow), one truncated
     // Shoup multiply brings the product to [0,4p), two conditional subtractions make it canonical
