@@ -582,9 +582,24 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         dst.jj[dst.n++] = (signed char)jj;
     }
     const bool special_small = (c->primes[K - 1] >> 41) == 0;
+    static const int ksplit_below = getenv("CKKS_KSPLIT_BELOW") ? atoi(getenv("CKKS_KSPLIT_BELOW")) : 3;
     for (int b0 = slot0; b0 < slot0 + nslots; b0 += Bc) {
         const int bc = (slot0 + nslots - b0) < Bc ? (slot0 + nslots - b0) : Bc;
         g_pdl_now = g_pdl_mode < 0 ? bc >= 8 : g_pdl_mode != 0;
+        // one or two ciphertexts (the GPU is mostly empty, latency is what counts -- e.g. the reference's own sequential
+        // programs on the shim): the special-prime limb's CTAs are the longest of the pipeline (L transforms + 2 INTT row
+        // passes); split them by key component over two CTAs (-9 % at batch 2).  From batch 4 on every kernel already has
+        // about one CTA per SM and extra CTAs only make the critical ones share an SM (+7 % at batch 4, measured).
+        JjList bigl = big;
+        if (fuse && !special_small && bc < ksplit_below && big.n > 0 && big.n < 35 && big.jj[0] == L) {
+            for (int q = bigl.n; q > 0; q--) {
+                bigl.jj[q] = bigl.jj[q - 1];
+                bigl.kh[q] = bigl.kh[q - 1];
+            }
+            bigl.n++;
+            bigl.kh[0] = 1;
+            bigl.kh[1] = 2;
+        }
         rt.b0 = b0;
         DView dD{D, (u64)L * N, 0};
         DView spec{ACC + (size_t)L * N, (u64)(L + 1) * N, 0};             // special-prime limb of every (b,k)
@@ -622,8 +637,8 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
             if (sfp != st) CU(cudaEventRecord(ln.join, sfp));                                                           \
         }                                                                                                               \
         if (big.n) {                                                                                                    \
-            if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, fuse, c->t); \
-            else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, big.n, bc), st, T1, rt, ACC, L, big, fuse, c->t);   \
+            if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, bigl.n, bc), st, T1, rt, ACC, L, bigl, fuse, c->t); \
+            else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, bigl.n, bc), st, T1, rt, ACC, L, bigl, fuse, c->t);   \
             LAUNCH_CHECK(c);                                                                                            \
         }                                                                                                               \
         /* a small special prime puts its limb on the side stream: the INTT below must wait for it */            \

@@ -405,6 +405,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_ks_invcol_modup(const u64 *D
 struct JjList {
     int n;
     signed char jj[36];
+    signed char kh[36];   // 0 = both key components in this CTA; 1 / 2 = only component 0 / 1 (the special-prime limb of a
+                          // small batch is split over two CTAs: each repeats the transforms but runs one INTT instead of two)
 };
 template <int LOGN, bool GALOIS>
 __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRoute rt, u64 *ACC, int L, JjList list, int fuse_inv, Tables t) {
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
     // TMA-staged input tiles of the current / next digit; the current one doubles as the exchange buffer
     __shared__ __align__(128) u64 stage[2][NTT_TILE];
     __shared__ u64 bars[2];
-    const int jj = list.jj[blockIdx.y], b = blockIdx.z;
+    const int jj = list.jj[blockIdx.y], kh = list.kh[blockIdx.y], b = blockIdx.z;
     const KsSel sl = route_sel(rt, b);
     const DView tgt = rt.v[sl.src];
     const uint32_t *__restrict__ perm = GALOIS ? route_perm(rt, sl) : nullptr;
@@ -472,12 +474,21 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
         const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + koff);
         const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + koff);
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
-            ulonglong2 a = __ldg(k0 + kstep * v), c = __ldg(k1 + kstep * v);
-            mac128(lo0[2 * v], hi0[2 * v], x[2 * v], a.x);
-            mac128(lo0[2 * v + 1], hi0[2 * v + 1], x[2 * v + 1], a.y);
-            mac128(lo1[2 * v], hi1[2 * v], x[2 * v], c.x);
-            mac128(lo1[2 * v + 1], hi1[2 * v + 1], x[2 * v + 1], c.y);
+        if (kh != 2) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                ulonglong2 a = __ldg(k0 + kstep * v);
+                mac128(lo0[2 * v], hi0[2 * v], x[2 * v], a.x);
+                mac128(lo0[2 * v + 1], hi0[2 * v + 1], x[2 * v + 1], a.y);
+            }
+        }
+        if (kh != 1) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                ulonglong2 c = __ldg(k1 + kstep * v);
+                mac128(lo1[2 * v], hi1[2 * v], x[2 * v], c.x);
+                mac128(lo1[2 * v + 1], hi1[2 * v + 1], x[2 * v + 1], c.y);
+            }
         }
     }
     PDL_LATE();
@@ -489,16 +500,20 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
         const tw_t *twi = t.twi + (size_t)pj * G::N;
         u64 r[8];
         __syncthreads();   // every thread is done with the exchange buffers of the last digit
+        if (kh != 2) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) r[e] = barrett128(lo0[e], hi0[e], m);
-        inv_row_pass<LOGN>(r, twi, m, t0, stage[0]);
+            for (int e = 0; e < 8; e++) r[e] = barrett128(lo0[e], hi0[e], m);
+            inv_row_pass<LOGN>(r, twi, m, t0, stage[0]);
 #pragma unroll
-        for (int e = 0; e < 8; e++) b0[row_strided_li<LOGN>(e)] = r[e];
+            for (int e = 0; e < 8; e++) b0[row_strided_li<LOGN>(e)] = r[e];
+        }
+        if (kh != 1) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) r[e] = barrett128(lo1[e], hi1[e], m);
-        inv_row_pass<LOGN>(r, twi, m, t0, stage[1]);
+            for (int e = 0; e < 8; e++) r[e] = barrett128(lo1[e], hi1[e], m);
+            inv_row_pass<LOGN>(r, twi, m, t0, stage[1]);
 #pragma unroll
-        for (int e = 0; e < 8; e++) b1[row_strided_li<LOGN>(e)] = r[e];
+            for (int e = 0; e < 8; e++) b1[row_strided_li<LOGN>(e)] = r[e];
+        }
         return;
     }
     u64 *o0 = ACC + (((u64)b * 2 + 0) * (L + 1) + jj) * G::N + t0 + 8 * threadIdx.x;
