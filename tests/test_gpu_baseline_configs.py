@@ -244,6 +244,14 @@ def test_config4_matmul_n16384_d64_decrypts_to_product(eng):
     assert got.size == 3 and got.limbs == 4
     dec = enc.decode(decr.decrypt(got))[0, :dd].reshape(d, d)
     assert np.abs(dec - A @ B).max() < 1e-2
+    # SURVEY 8(f4) tolerance mode: only the non-empty diagonals (~1.5 k key switches instead of 72 820): same product,
+    # without the reference's epsilon error term (so closer to A @ B), different ciphertext polynomials
+    fast = wl.cc_matrix_multiplication_nonzero(ev, ctA, ctB, d, sigma, tau, V, W, keys, plans)
+    assert fast.size == 3 and fast.limbs == got.limbs and fast.scale == got.scale
+    decf = enc.decode(decr.decrypt(fast))[0, :dd].reshape(d, d)
+    assert np.abs(decf - A @ B).max() < 1e-3
+    assert np.abs(decf - dec).max() < 1e-2
+    assert len(sigma.index) == 2 * d - 1 and len(tau.index) == d and all(len(v.index) == 2 for v in V) and all(len(w.index) == 1 for w in W)
 
 
 def test_config1_pulsar_real_data_update_weights(eng):
