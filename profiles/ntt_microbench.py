@@ -13,7 +13,7 @@ pkg = importlib.import_module(PKG)
 eng = pkg.load_engine()
 params = importlib.import_module(PKG + ".params")
 
-for log_n in (14, 15):
+for log_n in ((14,) if os.environ.get("CKKS_NTT_LIMB") else (14, 15)):
     primes = params.coeff_modulus_create(log_n, [60, 40, 40, 60])
     ctx = eng.Context(log_n, primes)
     ev = eng.Evaluator(ctx)

@@ -392,6 +392,30 @@ static int ntt_api(ckks_ctx *c, uint64_t *data, int n_polys, int limbs, int firs
     if (n_polys > 65535) return fail(CKKS_ERR_INVALID, "ntt: more than 65535 polys");
     CU(cudaSetDevice(c->device));
     DView v{(u64 *)data, ps, 0};
+    // north-star variant: one limb per CTA, limb resident in shared memory (N <= 16384); opt-in, see kernels.cuh
+    static const bool limb_per_cta = getenv("CKKS_NTT_LIMB") && atoi(getenv("CKKS_NTT_LIMB"));
+    if (limb_per_cta && c->log_n <= 14) {
+        const size_t smem = ((size_t)c->n + 4 * NTT_TILE) * 8;
+        const unsigned grid = (unsigned)n_polys * (unsigned)limbs;
+#define RUNL(LN)                                                                                                          \
+    {                                                                                                                     \
+        if (inverse) {                                                                                                    \
+            CU(cudaFuncSetAttribute(k_ntt_limb<LN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+            k_ntt_limb<LN, true><<<grid, 1024, smem, st>>>(v, limbs, first_prime, c->t);                                  \
+        } else {                                                                                                          \
+            CU(cudaFuncSetAttribute(k_ntt_limb<LN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+            k_ntt_limb<LN, false><<<grid, 1024, smem, st>>>(v, limbs, first_prime, c->t);                                 \
+        }                                                                                                                 \
+        LAUNCH_CHECK(c);                                                                                                  \
+    }
+        switch (c->log_n) {
+        case 12: RUNL(12); break;
+        case 13: RUNL(13); break;
+        default: RUNL(14); break;
+        }
+#undef RUNL
+        return CKKS_OK;
+    }
 #define RUN(LN)                                                                                             \
     {                                                                                                       \
         dim3 gc(NttGeo<LN>::COL_TILES, limbs, n_polys), gr(NttGeo<LN>::ROW_TILES, limbs, n_polys);          \

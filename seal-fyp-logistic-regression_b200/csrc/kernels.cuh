@@ -254,6 +254,119 @@ __global__ void __launch_bounds__(NTT_THREADS) k_inv_col(DView src, DView dst, i
     }
 }
 
+// ---- north-star variant (a): ONE RNS LIMB PER CTA, the limb resident in shared memory between the two passes (N <= 16384:
+// a limb is at most 128 KB; N = 32768 would need a 2-CTA cluster).  1024 threads = four groups of
+// 256 that run the same tile passes as the two-kernel transform, each group on its own tiles and exchange buffer, with the
+// 64 x N2 limb matrix in shared memory instead of HBM/L2 in between: one global read and one global write per limb.
+// Selected for the plain NTT entry points by CKKS_NTT_LIMB=1 (measured against the two-pass kernels in
+// profiles/r02_keyswitch_experiments.md).
+template <int LOGN, bool INVERSE>
+__global__ void __launch_bounds__(1024, 1) k_ntt_limb(DView v, int limbs, int first_prime, Tables t) {
+    typedef NttGeo<LOGN> G;
+    extern __shared__ __align__(16) u64 sm_limb[];            // [N] limb, then 4 x [NTT_TILE] exchange buffers
+    u64 *limb = sm_limb;
+    const int grp = threadIdx.x >> 8;
+    u64 *exch = sm_limb + G::N + grp * NTT_TILE;
+    const int l = blockIdx.x % limbs, pj = first_prime + l;
+    u64 *data = v.data + (u64)(blockIdx.x / limbs) * v.bs + (u64)l * G::N;
+    const ModConst m = load_mod(t, pj);
+    const FpConst f = t.fp[pj];
+    const bool fp = f.ok != 0.0;
+    u64 x[8];
+    double xd[8];
+    // every group runs the same number of passes (they share the CTA-wide barriers inside the pass functions): a group
+    // without a tile of its own in the last round repeats another tile and discards the result
+    constexpr int CROUNDS = (G::COL_TILES + 3) / 4, RROUNDS = (G::ROW_TILES + 3) / 4;
+    const unsigned tid = threadIdx.x & 255;
+    if (!INVERSE) {
+        for (int r = 0; r < CROUNDS; r++) {
+            const int tile = 4 * r + grp;
+            const bool active = tile < G::COL_TILES;
+            const int c0 = (active ? tile : tile % G::COL_TILES) * 32;
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = data[col_coarse_idx<LOGN>(c0, e)];
+            if (fp) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+                fwd_col_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, as_fp(exch));
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = fp_bits(xd[e]);
+            } else {
+                fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, exch);
+            }
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) limb[col_fine_idx<LOGN>(c0, e)] = x[e];
+            }
+            __syncthreads();   // exchange buffer reuse by this group's next tile; after the last round: limb complete
+        }
+        for (int r = 0; r < RROUNDS; r++) {
+            const int tile = 4 * r + grp;
+            const bool active = tile < G::ROW_TILES;
+            const int t0 = (active ? tile : tile % G::ROW_TILES) * NTT_TILE;
+            if (fp) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) xd[e] = bits_fp(limb[t0 + row_strided_li<LOGN>(e)]);
+                fwd_row_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, t0, as_fp(exch));
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = fp_to_canonical(xd[e], f);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = limb[t0 + row_strided_li<LOGN>(e)];
+                fwd_row_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, t0, exch);
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = reduce64(x[e], m);
+            }
+            if (active) store8(data + t0 + 8 * tid, x);
+            __syncthreads();
+        }
+    } else {
+        for (int r = 0; r < RROUNDS; r++) {
+            const int tile = 4 * r + grp;
+            const bool active = tile < G::ROW_TILES;
+            const int t0 = (active ? tile : tile % G::ROW_TILES) * NTT_TILE;
+            load8(x, data + t0 + 8 * tid);
+            if (fp) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+                inv_row_pass_fp<LOGN>(xd, t.twid + (size_t)pj * G::N, f, t0, as_fp(exch));
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = fp_bits(xd[e]);
+            } else {
+                inv_row_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m, t0, exch);
+            }
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) limb[t0 + row_strided_li<LOGN>(e)] = x[e];
+            }
+            __syncthreads();
+        }
+        for (int r = 0; r < CROUNDS; r++) {
+            const int tile = 4 * r + grp;
+            const bool active = tile < G::COL_TILES;
+            const int c0 = (active ? tile : tile % G::COL_TILES) * 32;
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = limb[col_fine_idx<LOGN>(c0, e)];
+            if (fp) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) xd[e] = bits_fp(x[e]);
+                inv_col_pass_fp<LOGN>(xd, t.twid + (size_t)pj * G::N, f, as_fp(exch));
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = fp_to_canonical(xd[e], f);
+            } else {
+                inv_col_pass<LOGN>(x, t.twi + (size_t)pj * G::N, m, exch);
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = csub(csub(x[e], m.p2), m.p);
+            }
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) data[col_coarse_idx<LOGN>(c0, e)] = x[e];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // =============================================================================== key switching
 // (1) digit INTT, row pass.  target limb i of ciphertext b: tgt.data + b*tgt.bs + i*N.
 // With GALOIS the Galois automorphism is applied while loading: in NTT form it is the pure

@@ -36,6 +36,10 @@ struct NttGeo {
 
 typedef ulonglong2 tw_t;  // {w, floor(w 2^64 / p)}
 
+// thread index inside the 256-thread group that owns a tile (the tile kernels are 256-thread CTAs: identity there; the
+// limb-per-CTA kernel runs four such groups in one 1024-thread CTA)
+__device__ __forceinline__ unsigned ntt_tid() { return threadIdx.x & (NTT_THREADS - 1); }
+
 // swizzled shared-memory index for the row pass: keeps every access pattern of the three radix
 // steps conflict-free for 64-bit words (bank pair = low 4 bits)
 __device__ __forceinline__ int sw(int li) { return li ^ ((li >> 3) & 15); }
@@ -107,19 +111,19 @@ __device__ __forceinline__ void inv8(u64 (&x)[8], const tw_t *__restrict__ tw, u
 //               row  (8k + e)  on the fine side     (stride 1 row)
 template <int LOGN>
 __device__ __forceinline__ int col_coarse_idx(int c0, int e) {
-    int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int k = ntt_tid() >> 5, lane = ntt_tid() & 31;
     return (k + 8 * e) * NttGeo<LOGN>::N2 + c0 + lane;
 }
 template <int LOGN>
 __device__ __forceinline__ int col_fine_idx(int c0, int e) {
-    int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int k = ntt_tid() >> 5, lane = ntt_tid() & 31;
     return (8 * k + e) * NttGeo<LOGN>::N2 + c0 + lane;
 }
 
 // forward: x holds the coarse-side elements (values < 8p); returns fine-side elements, lazy (< 8p + 2^32)
 template <int LOGN>
 __device__ __forceinline__ void fwd_col_pass(u64 (&x)[8], const tw_t *__restrict__ tw, const ModConst &m, u64 *smem) {
-    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = ntt_tid() >> 5, lane = ntt_tid() & 31;
     fwd8<0>(x, tw, 1u, m);  // stages 0..2, root node
     Tw8 t2;
     load_tw8<0>(t2, tw, 8u + k);   // in flight across the exchange
@@ -135,7 +139,7 @@ __device__ __forceinline__ void fwd_col_pass(u64 (&x)[8], const tw_t *__restrict
 // in [0,4p)
 template <int LOGN>
 __device__ __forceinline__ void inv_col_pass(u64 (&x)[8], const tw_t *__restrict__ twi, const ModConst &m, u64 *smem) {
-    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = ntt_tid() >> 5, lane = ntt_tid() & 31;
     inv8<0>(x, twi, 8u + k, m);  // stages 5..3
     Tw8 t2;
     load_tw8<1>(t2, twi, 1u);
@@ -162,16 +166,16 @@ __device__ __forceinline__ void inv_col_pass(u64 (&x)[8], const tw_t *__restrict
 template <int LOGN>
 __device__ __forceinline__ int row_strided_li(int e) {
     typedef NttGeo<LOGN> G;
-    int rr = threadIdx.x / G::T, k = threadIdx.x % G::T;
+    int rr = ntt_tid() / G::T, k = ntt_tid() % G::T;
     return rr * G::N2 + k + G::T * e;
 }
-__device__ __forceinline__ int row_contig_li(int e) { return 8 * (int)threadIdx.x + e; }
+__device__ __forceinline__ int row_contig_li(int e) { return 8 * (int)ntt_tid() + e; }
 
 template <int LOGN>
 __device__ __forceinline__ int row_mid_li(int e) {
     typedef NttGeo<LOGN> G;
     constexpr int T8 = G::T / 8;  // stride of the middle radix step
-    int rr = threadIdx.x / G::T, k = threadIdx.x % G::T;
+    int rr = ntt_tid() / G::T, k = ntt_tid() % G::T;
     int a = k / T8, k2 = k % T8;
     return rr * G::N2 + a * G::T + k2 + T8 * e;
 }
@@ -282,7 +286,7 @@ __device__ __forceinline__ void inv8d(double (&x)[8], const Tw8d &t, const FpCon
 // forward column pass: |x| grows by at most 2p per stage (12p over the pass)
 template <int LOGN>
 __device__ __forceinline__ void fwd_col_pass_fp(double (&x)[8], const double *__restrict__ tw, const FpConst &f, double *smem) {
-    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = ntt_tid() >> 5, lane = ntt_tid() & 31;
     Tw8d t1, t2;
     load_tw8d<0>(t1, tw, 1u);
     load_tw8d<0>(t2, tw, 8u + k);
@@ -297,7 +301,7 @@ __device__ __forceinline__ void fwd_col_pass_fp(double (&x)[8], const double *__
 // inverse column pass: inputs reduced (|x| < p), returns values scaled by N^-1 with |x| < 2p
 template <int LOGN>
 __device__ __forceinline__ void inv_col_pass_fp(double (&x)[8], const double *__restrict__ twi, const FpConst &f, double *smem) {
-    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = ntt_tid() >> 5, lane = ntt_tid() & 31;
     Tw8d t1, t2;
     load_tw8d<0>(t1, twi, 8u + k);
     load_tw8d<1>(t2, twi, 1u);

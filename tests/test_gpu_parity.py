@@ -39,6 +39,20 @@ def test_ntt_bit_exact_all_primes(make_fixture, eng, log_n):
     assert np.array_equal(t2.cpu().numpy().view(np.uint64), want_i)
 
 
+def test_ntt_limb_per_cta_variant_bit_exact():
+    """the north-star NTT variant (one RNS limb per CTA, limb resident in shared memory, CKKS_NTT_LIMB=1; N <= 16384) gives
+    the same bits as the oracle: the NTT parity tests above re-run in a child process with the variant selected"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CKKS_NTT_LIMB="1")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                          "-k", "test_ntt_bit_exact_all_primes or test_ntt_bfv_default_primes"], env=env, cwd=root,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "passed" in res.stdout, res.stdout[-2000:]
+
+
 def test_ntt_bfv_default_primes(po, eng):
     """config 2 chains: SEAL's BFVDefault primes for N = 4096 / 8192 (benchmark.cpp:137)"""
     import torch
