@@ -372,7 +372,10 @@ class Evaluator:
         return x
 
     def mod_switch_to(self, x, limbs):
-        """non-destructive: a new object sharing storage at the lower level"""
+        """non-destructive: a new object at the lower level that SHARES STORAGE with `x` (mod-switching is a metadata
+        change here; SEAL's mod_switch_to returns a copy).  Treat the result as read-only or .clone() it: an in-place op
+        on either object (add_inplace, multiply_plain_inplace, rescale with out=...) writes through to the other.  The
+        workloads in this package only read such views."""
         if limbs > x.limbs:
             raise capi.CkksInvalidArgument("cannot switch to higher level modulus")
         return Ciphertext(x.ctx, x.data, limbs, x.scale)
@@ -489,7 +492,9 @@ class Evaluator:
         return scratch if where.value else dup
 
     def multiply_plain_sum(self, cts, pts, out=None):
-        """multiply_plain of every batch entry with its plaintext, then add_many, in one kernel"""
+        """multiply_plain of every batch entry with its plaintext, then add_many, in one kernel.  (SEAL's per-product
+        "result ciphertext is transparent" check is not applied to the fused partial products; use multiply_plain(...,
+        check_transparent=True) where that error behaviour is wanted -- the reference's drivers avoid it with epsilon.)"""
         if cts.limbs != pts.limbs or cts.batch != pts.batch:
             raise capi.CkksInvalidArgument("encrypted and plain parameter mismatch")
         scale = cts.scale * pts.scale
