@@ -39,10 +39,9 @@ static int fail(int code, const std::string &msg) {
             return fail(CKKS_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
     } while (0)
 
-// Programmatic dependent launch: the next kernel of a pipeline may become resident while the
-// previous one drains; it runs its prologue (constants, first twiddles) and blocks at
-// griddepcontrol.wait until the predecessor's memory is visible.  Hides launch ramp-up between the
-// eight kernels of a key switch.
+// Programmatic dependent launch: the next kernel of a pipeline may become resident while the previous one drains; it runs
+// its prologue (constants, index tables) and blocks at griddepcontrol.wait until the predecessor's memory is visible.  The
+// kernels release their successor late (PDL_LATE in kernels.cuh), so only the immediate successor gets the head start.
 // -1 = automatic (on for launches that carry >= 8 ciphertexts), 0 = never, 1 = always (CKKS_PDL)
 static int g_pdl_mode = getenv("CKKS_PDL") ? atoi(getenv("CKKS_PDL")) : -1;
 static thread_local bool g_pdl_now = false;   // decided per batched key switch (keyswitch()), read by launch_pdl
@@ -84,7 +83,7 @@ struct ckks_ctx {
     size_t ws_bytes = 0;
     size_t ws_cap = size_t(1) << 30;
     uint64_t launches = 0;
-    // rotate-and-sum chains: private stream + cached CUDA graphs of two ping-pong steps
+    // rotate-and-sum chains: private streams + cached CUDA graphs of 1 and of 8 ping-pong pairs of steps
     cudaStream_t chain_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     // lane 0 is the normal path; lane 1 has its own workspace, side stream and events so that a chain can
@@ -926,7 +925,7 @@ extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const c
     if (count >= 4) {
         // two half-batches run as independent pipelines (lanes) on their own streams: the short kernels of
         // one lane (special-prime INTT: 1-2 waves) overlap the long ones of the other.  Each lane replays a
-        // cached CUDA graph of two ping-pong steps; the lanes only meet again at the end of the chain.
+        // cached CUDA graph of ping-pong steps; the lanes only meet again at the end of the chain.
         int nl = c->chain_lanes;
         while (nl > 1 && B / nl < 8) nl--;
         int split[5];
