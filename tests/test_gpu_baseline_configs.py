@@ -354,3 +354,31 @@ def test_gradient_unit_sharding_is_bit_identical(make_fixture):
     assert np.array_equal(combined.numpy(), full.numpy())
     dec = fx.orc.decode(fx.orc.decrypt(fx.sk, combined.numpy()[0]), combined.scale)[:C]
     assert np.abs(dec - X.T @ (lr.sigmoid_approx(X @ w0, degree) - y)).max() < 1e-2
+
+
+@pytest.mark.parametrize("L", [9, 3])
+def test_hoisted_rotations_on_the_bench_chain(fx_bench, L):
+    """ckks_rotate_plan_hoisted at N = 32768, K = 10 (integer limbs q_0 and P, FP64 limbs in between), top level and L = 3:
+    every hoisted rotation decrypts to the rotated slots like the SEAL-order rotation does (tolerance mode)"""
+    wl, _, _ = _mods()
+    fx = fx_bench
+    plans = wl.PlanCache(fx.ctx, fx.keys)
+    rng = np.random.default_rng(60 + L)
+    scale = 2.0 ** 40
+    x = rng.uniform(-1, 1, 256)
+    full = np.zeros(fx.n // 2)
+    full[:256] = x
+    ct = fx.ctx.upload(_enc(fx, 990 + L, x, scale)[:, :L], cap=fx.L, scale=scale)
+    plan = plans.get([1, -16, 0])
+    ref = fx.ev.rotate_plan(ct, plan)
+    got = fx.ev.rotate_plan_hoisted(ct, plan)
+    assert got.limbs == L and np.array_equal(got.numpy()[2], ct.numpy()[0])
+    for b, st in enumerate((1, -16)):
+        assert np.array_equal(ref.numpy()[b], fx.orc.rotate(ct.numpy()[0], st, fx.gks))     # the exact path, for reference
+        assert not np.array_equal(got.numpy()[b], ref.numpy()[b])
+        dg = fx.orc.decode(fx.orc.decrypt(fx.sk, got.numpy()[b]), scale)
+        dr = fx.orc.decode(fx.orc.decrypt(fx.sk, ref.numpy()[b]), scale)
+        # key-switch noise with a 60-bit q_0 digit against a 60-bit special prime is ~2^-19 at N = 32768 and scale 2^40 for
+        # SEAL's own rotation too: bound both by 2^-17 and the hoisted one by 4x the SEAL-order one
+        eg, er = np.abs(dg - np.roll(full, -st)).max(), np.abs(dr - np.roll(full, -st)).max()
+        assert er < 2.0 ** -17 and eg < 2.0 ** -17 and eg < 4 * er + 2.0 ** -22, (L, st, eg, er)

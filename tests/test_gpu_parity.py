@@ -387,3 +387,34 @@ def test_random_mixed_chains(make_fixture, bits):
         r = fx.orc.apply_galois(r, g, fx.gks[g])
         want = fx.orc.add(want, r)
     assert np.array_equal(acc.numpy()[0], want)
+
+
+def test_rotation_plan_survives_key_replacement(make_fixture):
+    """a rotation plan compiled before one of its Galois keys is replaced (KeySet.set_galois with a new buffer for the same
+    element) must use the NEW key at its next run -- the engine-owned copy of the old key is freed on replacement, and
+    plans used to keep its address"""
+    import importlib
+    wl = importlib.import_module("seal-fyp-logistic-regression_b200.workloads")
+    fx = make_fixture(12, CHAINS[12], steps=(1, -1, 2, -2, 4, 8))
+    eng, ctx, orc = fx.eng, fx.ctx, fx.orc
+    keys = eng.KeySet(ctx)                               # a private key set: the fixture's is shared by other tests
+    gks = dict(fx.gks)
+    for g, k in gks.items():
+        keys.set_galois(g, ctx.upload_key(k))
+    rng = np.random.default_rng(91)
+    a = fx.random_ct(rng, 1, 2, fx.L)
+    d = ctx.upload(a)
+    plan = wl.PlanCache(ctx, keys).get([1, 3, 6])
+    before = fx.ev.rotate_plan(d, plan).numpy()
+    for b, st in enumerate((1, 3, 6)):
+        assert np.array_equal(before[b], orc.rotate(a[0], st, gks))
+    # a different key for step 4 (another sample of the same key switch): replace it, run the SAME plan.
+    # NAF: 3 = {-1, 4} uses it, 1 and 6 = {-2, 8} do not
+    g4 = orc.galois_elt(4)
+    gks[g4] = orc.gen_galois_key(4242, fx.sk, g4)
+    assert not np.array_equal(gks[g4], fx.gks[g4])
+    keys.set_galois(g4, ctx.upload_key(gks[g4]))
+    after = fx.ev.rotate_plan(d, plan).numpy()
+    for b, st in enumerate((1, 3, 6)):
+        assert np.array_equal(after[b], orc.rotate(a[0], st, gks)), st
+    assert np.array_equal(after[0], before[0]) and np.array_equal(after[2], before[2]) and not np.array_equal(after[1], before[1])
