@@ -372,8 +372,14 @@ __global__ void __launch_bounds__(1024, 1) k_ntt_limb(DView v, int limbs, int fi
 // With GALOIS the Galois automorphism is applied while loading: in NTT form it is the pure
 // permutation out[g] = in[perm[g]] (SEAL util::apply_galois_ntt); perm maps each row of the
 // limb matrix into a single source row, so the gather stays inside one 0.5-4 KB segment.
+#ifndef V_OCC_INTT
+#define V_OCC_INTT 5
+#endif
+#ifndef V_OCC_COL
+#define V_OCC_COL 4
+#endif
 template <int LOGN, bool GALOIS>
-__global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_intt_row(KsRoute rt, u64 *D, int L, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, V_OCC_INTT) k_ks_intt_row(KsRoute rt, u64 *D, int L, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[NTT_TILE];
     const int i = blockIdx.y, b = blockIdx.z;
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_ks_modup_col(const u64 *D, u
 // grid: (COL_TILES, L * nsplit, batch); part p of a digit handles its targets p, p + nsplit, ...
 // (nsplit > 1 trades a repeated inverse pass for more CTAs when the batch is too small to fill the GPU).
 template <int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_ks_invcol_modup(const u64 *D, u64 *T1, int L, int nsplit, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, V_OCC_COL) k_ks_invcol_modup(const u64 *D, u64 *T1, int L, int nsplit, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[2][NTT_TILE];   // alternating exchange buffers: no barrier needed between passes
     const int i = blockIdx.y / nsplit, part = blockIdx.y % nsplit, b = blockIdx.z;
@@ -814,7 +820,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 5) k_md_fwd_col(DView R, u64 *T2,
 // column pass of (r' mod q_j) - (half mod q_j) for every remaining prime j.
 // grid: (COL_TILES, nsplit, instances); part p handles j = p, p + nsplit, ...
 template <int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_md_invcol_fwdcol(DView R, u64 *T2, int Lout, int a, int nsplit, Tables t) {
+__global__ void __launch_bounds__(NTT_THREADS, V_OCC_COL) k_md_invcol_fwdcol(DView R, u64 *T2, int Lout, int a, int nsplit, Tables t) {
     typedef NttGeo<LOGN> G;
     __shared__ u64 smem[2][NTT_TILE];
     const int part = blockIdx.y, z = blockIdx.z;
