@@ -145,6 +145,34 @@ inline seal::Ciphertext Linear_Transform_Plain(const seal::Ciphertext &ct, const
     return out;
 }
 
+// SURVEY 8(f4), opt-in: Linear_Transform_Plain with HOISTED rotations -- the d-1 rotations of the hot loop (helper.h:252-257)
+// all act on the same ct_new, so its digit decomposition is shared (ckks_rotate_plan_hoisted).  gal_keys must hold a key for
+// every step 1..d-1 themselves and for -d (keygen.galois_keys(steps)).  The result decrypts like Linear_Transform_Plain's within
+// key-switch noise; its polynomials are NOT SEAL's (SEAL permutes before lifting digits), hence a separate function.
+inline seal::Ciphertext Linear_Transform_Plain_hoisted(const seal::Ciphertext &ct, const std::vector<seal::Plaintext> &U_diagonals,
+                                                       const seal::GaloisKeys &gal_keys, const seal::EncryptionParameters &params) {
+    auto context = seal::SEALContext::Create(params);
+    seal::Evaluator evaluator(context);
+    const int d = (int)U_diagonals.size();
+    detail::Batch diags = detail::gather(U_diagonals);
+    seal::Ciphertext ct_new = detail::duplicate(ct, d, gal_keys, evaluator);
+    const detail::Poly &pn = ct_new.poly();
+    if (pn.limbs != diags.limbs) throw std::invalid_argument("encrypted and plain parameter mismatch");
+    detail::scale_ok(*pn.eng, pn.scale * diags.scale, pn.limbs);
+    std::vector<int> steps(d);
+    for (int l = 0; l < d; l++) steps[l] = l;
+    detail::Plan plan(pn.eng, gal_keys, steps);
+    detail::Batch rots(pn.eng, d, 2, pn.limbs, pn.scale);
+    ckks_view vi = pn.view(), vr = rots.view();
+    detail::check(ckks_rotate_plan_hoisted(pn.eng->ctx, plan.p, &vi, &vr, nullptr));
+    seal::Ciphertext out;
+    out.poly().allocate(pn.eng, 2, pn.limbs);
+    out.poly().scale = pn.scale * diags.scale;
+    ckks_view vd = diags.view(), vo = out.poly().view();
+    detail::check(ckks_multiply_plain_sum(pn.eng->ctx, &vr, &vd, &vo, nullptr));
+    return out;
+}
+
 // helper.h:212-234 -- the same with ciphertext diagonals; the result has size 3 (no relinearisation)
 inline seal::Ciphertext Linear_Transform_Cipher(const seal::Ciphertext &ct, const std::vector<seal::Ciphertext> &U_diagonals,
                                                 const seal::GaloisKeys &gal_keys, seal::Evaluator &evaluator) {

@@ -99,6 +99,26 @@ int main() {
         if (!(err < 1e-4)) failures++;
     }
 
+    {   // SURVEY 8(f4) opt-in mode from C++: hoisted rotations (needs a key per step): same decrypted product, different polynomials
+        vector<int> hsteps{-d};
+        for (int l = 1; l < d; l++) hsteps.push_back(l);
+        GaloisKeys gk_h = keygen.galois_keys(hsteps);
+        Ciphertext h;
+        double t_h = timed(h, eng, [&] { return b200::Linear_Transform_Plain_hoisted(cv, diag_pt, gk_h, params); });
+        Plaintext p;
+        vector<double> out;
+        decryptor.decrypt(h, p);
+        encoder.decode(p, out);
+        double err = 0;
+        for (int i = 0; i < d; i++) {
+            double want = 0;
+            for (int j = 0; j < d; j++) want += U[i][j] * v[j];
+            err = max(err, fabs(out[i] - want));
+        }
+        cout << "  b200::Linear_Transform_Plain_hoisted (d = 12): " << t_h << " us, max |decrypt - U v| = " << err << endl;
+        if (!(err < 1e-4)) failures++;
+    }
+
     t_ref = timed(ref, eng, [&] { return Linear_Transform_Cipher(cv, diag_ct, gk, evaluator); });
     t_got = timed(got, eng, [&] { return b200::Linear_Transform_Cipher(cv, diag_ct, gk, evaluator); });
     same("Linear_Transform_Cipher (d = 12)", ref, got, t_ref, t_got);
