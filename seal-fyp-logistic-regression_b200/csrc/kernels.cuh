@@ -1139,6 +1139,12 @@ __device__ __forceinline__ ulonglong2 *vpw(const DView &v, int b, int s, int j, 
     return reinterpret_cast<ulonglong2 *>(v.data + b * v.bs + s * v.ps + (u64)j * n + c);
 }
 
+// x * y mod p for canonical operands of a prime below 2^41, on the FP64 pipe (6 exact operations instead of the ~10 wide
+// integer multiplies of a 128-bit product + Barrett reduction): keeps the element-wise products memory-bound
+__device__ __forceinline__ u64 fp_mulmod_u64(u64 x, u64 y, const FpConst &f) {
+    return fp_to_canonical(fp_mulmod(fp_from_u64(x), fp_from_u64(y), f), f);
+}
+
 // OP 0 add, 1 sub, 2 negate (b unused)
 template <int OP>
 __global__ void __launch_bounds__(256) k_ew_addsub(DView a, DView b, DView o, int L, int n, Tables t) {
@@ -1155,8 +1161,14 @@ __global__ void __launch_bounds__(256) k_ew_addsub(DView a, DView b, DView o, in
 __global__ void __launch_bounds__(256) k_ew_mul_plain(DView ct, DView pt, DView o, int L, int n, Tables t) {
     EW_PROLOGUE(L)
     ulonglong2 x = *vp(ct, blockIdx.z, s, j, n, c), y = *vp(pt, blockIdx.z, 0, j, n, c), r;
-    r.x = mulmod(x.x, y.x, m);
-    r.y = mulmod(x.y, y.y, m);
+    const FpConst f = t.fp[j];
+    if (f.ok != 0.0) {
+        r.x = fp_mulmod_u64(x.x, y.x, f);
+        r.y = fp_mulmod_u64(x.y, y.y, f);
+    } else {
+        r.x = mulmod(x.x, y.x, m);
+        r.y = mulmod(x.y, y.y, m);
+    }
     *vpw(o, blockIdx.z, s, j, n, c) = r;
 }
 
@@ -1184,6 +1196,31 @@ __global__ void __launch_bounds__(256) k_ew_multiply(DView a, DView b, DView o, 
     for (int i = 0; i < SA; i++) xa[i] = *vp(a, blockIdx.z, i, j, n, c);
 #pragma unroll
     for (int i = 0; i < SB; i++) xb[i] = *vp(b, blockIdx.z, i, j, n, c);
+    const FpConst f = t.fp[j];
+    if (f.ok != 0.0) {   // small prime: products and their sums as exact doubles (at most 3 terms of magnitude < 2p each)
+        double ax[SA], ay[SA], bx[SB], by[SB];
+#pragma unroll
+        for (int i = 0; i < SA; i++) { ax[i] = fp_from_u64(xa[i].x); ay[i] = fp_from_u64(xa[i].y); }
+#pragma unroll
+        for (int i = 0; i < SB; i++) { bx[i] = fp_from_u64(xb[i].x); by[i] = fp_from_u64(xb[i].y); }
+#pragma unroll
+        for (int k = 0; k < SA + SB - 1; k++) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < SA; i++) {
+                const int l = k - i;
+                if (l >= 0 && l < SB) {
+                    s0 = __dadd_rn(s0, fp_mulmod(ax[i], bx[l], f));
+                    s1 = __dadd_rn(s1, fp_mulmod(ay[i], by[l], f));
+                }
+            }
+            ulonglong2 r;
+            r.x = fp_to_canonical(s0, f);
+            r.y = fp_to_canonical(s1, f);
+            *vpw(o, blockIdx.z, k, j, n, c) = r;
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < SA + SB - 1; k++) {
         u64 l0 = 0, h0 = 0, l1 = 0, h1 = 0;
@@ -1225,6 +1262,48 @@ __global__ void __launch_bounds__(256) k_ew_mul_sum(DView a, DView b, DView o, i
     const u64 c = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (c >= (u64)n) return;
     const ModConst m = t.mod[j];
+    const FpConst f = t.fp[j];
+    if (f.ok != 0.0) {
+        // small prime: every product reduced on the FP64 pipe (|term| < 2p), running sums exact in doubles, brought back
+        // below p every 256 terms (256 * 2p < 2^50)
+        if (PLAIN) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int q = 0; q < B; q++) {
+                ulonglong2 x = *vp(a, q, s, j, n, c), y = *vp(b, q, 0, j, n, c);
+                s0 = __dadd_rn(s0, fp_mulmod(fp_from_u64(x.x), fp_from_u64(y.x), f));
+                s1 = __dadd_rn(s1, fp_mulmod(fp_from_u64(x.y), fp_from_u64(y.y), f));
+                if ((q & 255) == 255) { s0 = fp_reduce(s0, f); s1 = fp_reduce(s1, f); }
+            }
+            ulonglong2 r;
+            r.x = fp_to_canonical(s0, f);
+            r.y = fp_to_canonical(s1, f);
+            *vpw(o, 0, s, j, n, c) = r;
+        } else {
+            double sx[3] = {0.0, 0.0, 0.0}, sy[3] = {0.0, 0.0, 0.0};
+            for (int q = 0; q < B; q++) {
+                ulonglong2 a0 = *vp(a, q, 0, j, n, c), a1 = *vp(a, q, 1, j, n, c);
+                ulonglong2 b0 = *vp(b, q, 0, j, n, c), b1 = *vp(b, q, 1, j, n, c);
+                const double a0x = fp_from_u64(a0.x), a0y = fp_from_u64(a0.y), a1x = fp_from_u64(a1.x), a1y = fp_from_u64(a1.y);
+                const double b0x = fp_from_u64(b0.x), b0y = fp_from_u64(b0.y), b1x = fp_from_u64(b1.x), b1y = fp_from_u64(b1.y);
+                sx[0] = __dadd_rn(sx[0], fp_mulmod(a0x, b0x, f)); sy[0] = __dadd_rn(sy[0], fp_mulmod(a0y, b0y, f));
+                sx[1] = __dadd_rn(sx[1], __dadd_rn(fp_mulmod(a0x, b1x, f), fp_mulmod(a1x, b0x, f)));
+                sy[1] = __dadd_rn(sy[1], __dadd_rn(fp_mulmod(a0y, b1y, f), fp_mulmod(a1y, b0y, f)));
+                sx[2] = __dadd_rn(sx[2], fp_mulmod(a1x, b1x, f)); sy[2] = __dadd_rn(sy[2], fp_mulmod(a1y, b1y, f));
+                if ((q & 127) == 127) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { sx[k] = fp_reduce(sx[k], f); sy[k] = fp_reduce(sy[k], f); }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                ulonglong2 r;
+                r.x = fp_to_canonical(sx[k], f);
+                r.y = fp_to_canonical(sy[k], f);
+                *vpw(o, 0, k, j, n, c) = r;
+            }
+        }
+        return;
+    }
     if (PLAIN) {
         u64 l0 = 0, h0 = 0, l1 = 0, h1 = 0;
         for (int q = 0; q < B; q++) {
