@@ -497,17 +497,17 @@ __global__ void __launch_bounds__(NTT_THREADS, V_OCC_COL) k_ks_invcol_modup(cons
         // below 8 q_j, so the Barrett reduction is needed only for a much larger source prime
         const bool need_reduce = mi.p >= m.p4;
         u64 *out = T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N;
-        u64 x[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = need_reduce ? reduce64(v[e], m) : v[e];
-        if (f.ok != 0.0) {   // x < 4 q_j < 2^43: exact as doubles
+        if (f.ok != 0.0) {   // a congruent double below 2^43 in magnitude: the reduction of a large source prime stays on the FP64 pipe
             double xd[8];
 #pragma unroll
-            for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+            for (int e = 0; e < 8; e++) xd[e] = need_reduce ? fp_reduce_big(v[e], f) : fp_from_u64(v[e]);
             fwd_col_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, as_fp(smem[buf]));
 #pragma unroll
             for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = fp_bits(xd[e]);
         } else {
+            u64 x[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = need_reduce ? reduce64(v[e], m) : v[e];
             fwd_col_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, smem[buf]);
 #pragma unroll
             for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];
@@ -853,17 +853,19 @@ __global__ void __launch_bounds__(NTT_THREADS, V_OCC_COL) k_md_invcol_fwdcol(DVi
         const u64 hm = t.round_half ? t.halfmod[a * t.K + j] : 0;
         const bool need_reduce = ma.p >= m.p4;   // else r' + q_j - hm < 8 q_j is already a valid lazy input
         u64 *out = T2 + ((u64)z * Lout + j) * G::N;
-        u64 x[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = need_reduce ? submod(reduce64(v[e], m), hm, m.p) : v[e] + m.p - hm;
-        if (f.ok != 0.0) {   // x < 5 q_j: exact as doubles
+        if (f.ok != 0.0) {   // a congruent double below 2^43 in magnitude (the row pass canonicalises)
             double xd[8];
+            const double hmd = fp_from_u64(hm);
 #pragma unroll
-            for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+            for (int e = 0; e < 8; e++)
+                xd[e] = need_reduce ? __dadd_rn(fp_reduce_big(v[e], f), -hmd) : fp_from_u64(v[e] + m.p - hm);
             fwd_col_pass_fp<LOGN>(xd, t.twfd + (size_t)j * G::N, f, as_fp(smem[buf]));
 #pragma unroll
             for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = fp_bits(xd[e]);
         } else {
+            u64 x[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = need_reduce ? submod(reduce64(v[e], m), hm, m.p) : v[e] + m.p - hm;
             fwd_col_pass<LOGN>(x, t.twf + (size_t)j * G::N, m, smem[buf]);
 #pragma unroll
             for (int e = 0; e < 8; e++) out[col_fine_idx<LOGN>(c0, e)] = x[e];

@@ -154,7 +154,7 @@ __device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, u64 w, u64 ws, const Mod
 // butterflies add at most 2p per stage, inverse sums double per stage and are reduced once per pass.
 // Results are bit-identical to the integer path because only exact integer arithmetic is used.
 struct FpConst {
-    double p, pinv, ninv, w1ni, ok, pad;
+    double p, pinv, ninv, w1ni, ok, c31;   // c31 = 2^31 mod p
 };
 __device__ __forceinline__ double fp_rint(double v) {   // round to nearest integer, |v| < 2^51
     const double M = 6755399441055744.0;                 // 1.5 * 2^52
@@ -180,6 +180,11 @@ __device__ __forceinline__ double fp_reduce(double x, const FpConst &f) {
 // exact conversions for integers below 2^52
 __device__ __forceinline__ double fp_from_u64(u64 v) {
     return __dadd_rn(__longlong_as_double((long long)(v | 0x4330000000000000ull)), -4503599627370496.0);
+}
+// canonical residue of a large prime (v < 2^62) -> a double congruent to it modulo the small prime, |.| < 2p + 2^31
+__device__ __forceinline__ double fp_reduce_big(u64 v, const FpConst &f) {
+    const double hi = fp_from_u64(v >> 31), lo = fp_from_u64(v & 0x7fffffffull);
+    return __dadd_rn(fp_mulmod(hi, f.c31, f), lo);
 }
 __device__ __forceinline__ u64 fp_to_canonical(double x, const FpConst &f) {   // -> [0,p)
     double v = fp_reduce(x, f);

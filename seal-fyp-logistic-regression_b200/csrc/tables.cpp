@@ -129,6 +129,7 @@ void build_tables(int log_n, const std::vector<uint64_t> &primes, HostTables &ou
             f[2] = (double)n_inv;
             f[3] = (double)m[6];
             f[4] = 1.0;
+            f[5] = (double)((uint64_t(1) << 31) % p);
             for (size_t node = 0; node < n; ++node) {
                 out.twfd[j * n + node] = (double)tf[2 * node];
                 out.twid[j * n + node] = (double)ti[2 * node];

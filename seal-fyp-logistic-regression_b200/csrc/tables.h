@@ -13,7 +13,7 @@ struct HostTables {
     std::vector<uint64_t> invs;     // [K][K]  Shoup companions
     std::vector<uint64_t> halfmod;  // [K][K]  (q_a >> 1) mod q_j
     // FP64 butterfly path for primes below 2^41 (see modarith.cuh): per prime {p, 1/p, N^-1, w1*N^-1, ok}
-    std::vector<double> fpc;        // [K][6]  (ok stored as 1.0 / 0.0, one pad)
+    std::vector<double> fpc;        // [K][6]  (ok stored as 1.0 / 0.0, then 2^31 mod p)
     std::vector<double> twfd;       // [K][N]  forward twiddle tree as doubles (zero for large primes)
     std::vector<double> twid;       // [K][N]  inverse twiddle tree as doubles
 };
