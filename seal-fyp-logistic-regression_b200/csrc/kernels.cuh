@@ -372,6 +372,11 @@ __global__ void __launch_bounds__(1024, 1) k_ntt_limb(DView v, int limbs, int fi
 // With GALOIS the Galois automorphism is applied while loading: in NTT form it is the pure
 // permutation out[g] = in[perm[g]] (SEAL util::apply_galois_ntt); perm maps each row of the
 // limb matrix into a single source row, so the gather stays inside one 0.5-4 KB segment.
+#ifdef V_NOLOAD   // experiment only: input words synthesised instead of loaded = upper bound of any prefetch / staging scheme
+#define VLOAD(e, expr) ((u64)(threadIdx.x * 8u + (e) + blockIdx.x) & 0xffffffffull)
+#else
+#define VLOAD(e, expr) (expr)
+#endif
 #ifndef V_OCC_INTT
 #define V_OCC_INTT 5
 #endif
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(NTT_THREADS, V_OCC_INTT) k_ks_intt_row(KsRoute
         load_perm8(ix, perm + t0 + 8 * threadIdx.x);   // static table: before the dependency wait
         pdl_wait();
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = in[ix[e]];
+        for (int e = 0; e < 8; e++) x[e] = VLOAD(e, in[ix[e]]);
     } else {
         pdl_wait();
         load8(x, in + t0 + 8 * threadIdx.x);
@@ -472,7 +477,7 @@ __global__ void __launch_bounds__(NTT_THREADS, V_OCC_COL) k_ks_invcol_modup(cons
     u64 v[8];
     pdl_wait();
 #pragma unroll
-    for (int e = 0; e < 8; e++) v[e] = in[col_fine_idx<LOGN>(c0, e)];
+    for (int e = 0; e < 8; e++) v[e] = VLOAD(e, in[col_fine_idx<LOGN>(c0, e)]);
     if (fi.ok != 0.0) {
         double xd[8];
 #pragma unroll
@@ -832,7 +837,7 @@ __global__ void __launch_bounds__(NTT_THREADS, V_OCC_COL) k_md_invcol_fwdcol(DVi
     u64 v[8];
     pdl_wait();
 #pragma unroll
-    for (int e = 0; e < 8; e++) v[e] = in[col_fine_idx<LOGN>(c0, e)];
+    for (int e = 0; e < 8; e++) v[e] = VLOAD(e, in[col_fine_idx<LOGN>(c0, e)]);
     if (fa.ok != 0.0) {
         double xd[8];
 #pragma unroll
@@ -898,7 +903,7 @@ __global__ void __launch_bounds__(NTT_THREADS, V_MDROW_OCC) k_md_fwd_row(const u
     const FpConst f = t.fp[j];
     pdl_wait();
 #pragma unroll
-    for (int e = 0; e < 8; e++) x[e] = in[t0 + row_strided_li<LOGN>(e)];
+    for (int e = 0; e < 8; e++) x[e] = VLOAD(e, in[t0 + row_strided_li<LOGN>(e)]);
     const u64 *mi = minuend.data + b * minuend.bs + s * minuend.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
     u64 *out = dst.data + sl.entry * dst.bs + s * dst.ps + (u64)j * G::N + t0 + 8 * threadIdx.x;
     u64 mv[8], bv[8];
@@ -916,18 +921,25 @@ __global__ void __launch_bounds__(NTT_THREADS, V_MDROW_OCC) k_md_fwd_row(const u
     }
     // all epilogue loads are issued before the first store (out may alias base, so the compiler
     // would otherwise serialise load -> store -> load ...)
-#ifndef V_MDROW_EARLY
-    load8(mv, mi);
-#endif
-    if (MODE == 1) {
-        load8(bv, base.data + sl.entry * base.bs + s * base.ps + (u64)j * G::N + t0 + 8 * threadIdx.x);
-    } else if (MODE == 2) {
-        if (s == 0) {
-            unsigned ix[8];
-            load_perm8(ix, perm + t0 + 8 * threadIdx.x);
-            const u64 *bp = base.data + sl.entry * base.bs + (u64)j * G::N;
+#ifdef V_NOLOAD
 #pragma unroll
-            for (int e = 0; e < 8; e++) bv[e] = bp[ix[e]];
+    for (int e = 0; e < 8; e++) mv[e] = VLOAD(e, 0) + 5, bv[e] = VLOAD(e, 0) + 9;
+    if (false)
+#endif
+    {
+#ifndef V_MDROW_EARLY
+        load8(mv, mi);
+#endif
+        if (MODE == 1) {
+            load8(bv, base.data + sl.entry * base.bs + s * base.ps + (u64)j * G::N + t0 + 8 * threadIdx.x);
+        } else if (MODE == 2) {
+            if (s == 0) {
+                unsigned ix[8];
+                load_perm8(ix, perm + t0 + 8 * threadIdx.x);
+                const u64 *bp = base.data + sl.entry * base.bs + (u64)j * G::N;
+#pragma unroll
+                for (int e = 0; e < 8; e++) bv[e] = bp[ix[e]];
+            }
         }
     }
     PDL_LATE();
