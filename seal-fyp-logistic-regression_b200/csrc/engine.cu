@@ -62,6 +62,30 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t 
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// thread-block-cluster launch (cluster = grid.x CTAs: the digits of one output tile), dynamic shared memory opted in once
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, size_t smem, cudaStream_t st, Args... args) {
+    static thread_local std::map<const void *, bool> ready;
+    if (!ready[(const void *)kernel]) {
+        cudaError_t e = cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        ready[(const void *)kernel] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NTT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = grid.x;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------------------------ context
 struct ckks_ctx {
     int log_n = 0, n = 0, K = 0, device = 0;
@@ -606,6 +630,13 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
     }
     const bool special_small = (c->primes[K - 1] >> 41) == 0;
     static const int ksplit_below = getenv("CKKS_KSPLIT_BELOW") ? atoi(getenv("CKKS_KSPLIT_BELOW")) : 3;
+    // ciphertexts per launch below which the inner product runs as thread-block clusters over the digits (k_ks_mac_cl).
+    // Measured (profiles/r02_keyswitch_experiments.md): for a single ciphertext (the reference's own sequential programs on
+    // the shim) -10 % latency at N = 16384, L = 3 (-4 % at L = 2, N = 8192; -3 % at N = 4096), equal at N = 32768, +18 % with a
+    // single digit, slower from two ciphertexts on -- hence the default below; CKKS_CLUSTER_BELOW=n forces it for every
+    // launch of fewer than n ciphertexts at any degree and level.
+    static const int cluster_env = getenv("CKKS_CLUSTER_BELOW") ? atoi(getenv("CKKS_CLUSTER_BELOW")) : -1;
+    const int cluster_below = cluster_env >= 0 ? cluster_env : (c->log_n <= 14 && L >= 2 ? 2 : 0);
     for (int b0 = slot0; b0 < slot0 + nslots; b0 += Bc) {
         const int bc = (slot0 + nslots - b0) < Bc ? (slot0 + nslots - b0) : Bc;
         g_pdl_now = g_pdl_mode < 0 ? bc >= 8 : g_pdl_mode != 0;
@@ -648,8 +679,15 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
         }                                                                                                               \
         /* the FP64 inner product (small-prime limbs) is independent of the integer one and of the special-prime  \
            INTT that follows: fork it onto the side stream, join before the last kernel reads its output */       \
-        cudaStream_t sfp = (big.n && small.n) ? ln.side : st;                                                          \
-        if (small.n) {                                                                                                  \
+        const bool use_cl = fuse && bc < cluster_below && L <= 8 && (long)(L + 1) * bc <= 65535;                       \
+        cudaStream_t sfp = (big.n && small.n && !use_cl) ? ln.side : st;                                               \
+        if (use_cl) {                                                                                                   \
+            /* small batch: one cluster of L CTAs per output tile (k_ks_mac_cl), integer and FP64 limbs in one launch */ \
+            if (mode == 2) CU(launch_cluster(k_ks_mac_cl<LN, true>, dim3(L, G::ROW_TILES, (L + 1) * bc), 65536, st, T1, rt, ACC, L, fuse, c->t)); \
+            else CU(launch_cluster(k_ks_mac_cl<LN, false>, dim3(L, G::ROW_TILES, (L + 1) * bc), 65536, st, T1, rt, ACC, L, fuse, c->t)); \
+            LAUNCH_CHECK(c);                                                                                            \
+        }                                                                                                               \
+        if (small.n && !use_cl) {                                                                                                  \
             if (sfp != st) {                                                                                            \
                 CU(cudaEventRecord(ln.fork, st));                                                                       \
                 CU(cudaStreamWaitEvent(sfp, ln.fork, 0));                                                               \
@@ -659,7 +697,7 @@ static int keyswitch(ckks_ctx *c, int mode, int L, int nslots, KsRoute rt, cudaS
             LAUNCH_CHECK(c);                                                                                            \
             if (sfp != st) CU(cudaEventRecord(ln.join, sfp));                                                           \
         }                                                                                                               \
-        if (big.n) {                                                                                                    \
+        if (big.n && !use_cl) {                                                                                         \
             if (mode == 2) launch_pdl(k_ks_mac<LN, true>, dim3(G::ROW_TILES, bigl.n, bc), st, T1, rt, ACC, L, bigl, fuse, c->t); \
             else launch_pdl(k_ks_mac<LN, false>, dim3(G::ROW_TILES, bigl.n, bc), st, T1, rt, ACC, L, bigl, fuse, c->t);   \
             LAUNCH_CHECK(c);                                                                                            \

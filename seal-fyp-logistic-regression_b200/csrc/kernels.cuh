@@ -11,6 +11,7 @@
 // Grid conventions: blockIdx.x = tile inside a limb, blockIdx.y = limb / (digit,limb) pair,
 // blockIdx.z = ciphertext (or ciphertext*poly) index.  All CTAs are NTT_THREADS threads.
 #pragma once
+#include <cooperative_groups.h>
 #include "ntt_passes.cuh"
 
 struct Tables {
@@ -782,6 +783,155 @@ __global__ void __launch_bounds__(NTT_THREADS, V_MACFP_OCC) k_ks_mac_fp(const u6
     }
     store8(ACC + (((u64)b * 2 + 0) * (L + 1) + jj) * G::N + t0 + 8 * threadIdx.x, r0);
     store8(ACC + (((u64)b * 2 + 1) * (L + 1) + jj) * G::N + t0 + 8 * threadIdx.x, r1);
+}
+
+// (4c) small-batch variant of the inner product on a thread-block cluster: the L digits of one output tile go to the L
+// CTAs of a cluster (blockIdx.x = digit = cluster rank) instead of one CTA looping over them.  Each CTA transforms its digit,
+// multiplies it with its two key words and parks the 16 products per thread in its own shared memory; after a cluster
+// barrier rank k (k = 0, 1) sums component k over all ranks through distributed shared memory, reduces, and -- for the
+// special-prime limb -- continues into the mod-down INTT's row pass.  The critical path of the pipeline's longest kernel
+// drops from L transforms + 2 inverse passes to 1 + 1.  Same sums (exact integer / integer-valued FP64 arithmetic), so the
+// result is bit-identical to k_ks_mac / k_ks_mac_fp.  Dynamic shared memory: 64 KB ([2][8][256] x (lo, hi); the first
+// 16 KB double as the exchange buffer of the forward pass, the component-k block as that of rank k's inverse pass).
+template <int LOGN, bool GALOIS>
+__global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_cl(const u64 *T1, KsRoute rt, u64 *ACC, int L, int fuse_inv, Tables t) {
+    typedef NttGeo<LOGN> G;
+    extern __shared__ __align__(128) u64 dsm[];
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    const int i = blockIdx.x, jj = blockIdx.z % (L + 1), b = blockIdx.z / (L + 1), tid = threadIdx.x;
+    const KsSel sl = route_sel(rt, b);
+    const DView tgt = rt.v[sl.src];
+    const uint32_t *__restrict__ perm = GALOIS ? route_perm(rt, sl) : nullptr;
+    const u64 *__restrict__ ksk = route_key(rt, sl);
+    const int K = t.K, pj = jj == L ? K - 1 : jj;
+    const ModConst m = load_mod(t, pj);
+    const FpConst f = t.fp[pj];
+    const bool fp = f.ok != 0.0;
+    const int t0 = blockIdx.y * NTT_TILE;
+    const int koff = rt.key_tiled ? 2 * tid : 8 * tid, kstep = rt.key_tiled ? 256 : 1;
+    const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + koff);
+    const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + koff);
+    prefetch_l2(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * tid);
+    prefetch_l2(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * tid);
+    pdl_wait();
+    u64 x[8];
+    double xd[8];
+    if (i == pj) {   // the digit's own prime: the NTT-form limb of the target itself
+        const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
+        if (GALOIS) {
+            unsigned ix[8];
+            load_perm8(ix, perm + t0 + 8 * tid);
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = in[ix[e]];
+        } else {
+            load8(x, in + t0 + 8 * tid);
+        }
+        if (fp) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) xd[e] = fp_from_u64(x[e]);
+        }
+    } else {
+        const u64 *tile = T1 + (((u64)b * L + i) * (L + 1) + jj) * G::N + t0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = tile[row_strided_li<LOGN>(e)];
+        if (fp) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) xd[e] = bits_fp(x[e]);
+            fwd_row_pass_fp<LOGN>(xd, t.twfd + (size_t)pj * G::N, f, t0, as_fp(dsm));
+        } else {
+            fwd_row_pass<LOGN>(x, t.twf + (size_t)pj * G::N, m, t0, dsm);
+        }
+        __syncthreads();   // the exchange buffer is about to receive products
+    }
+    PDL_LATE();
+    const int n_k = L < 2 ? 2 : 1;   // components this rank finishes (a single-digit key switch: rank 0 does both)
+    if (fp) {
+        double *pr = as_fp(dsm);     // [2][8][256]
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            ulonglong2 a = __ldg(k0 + kstep * v), c = __ldg(k1 + kstep * v);
+            const double kax = rt.key_tiled ? bits_fp(a.x) : fp_from_u64(a.x), kay = rt.key_tiled ? bits_fp(a.y) : fp_from_u64(a.y);
+            const double kcx = rt.key_tiled ? bits_fp(c.x) : fp_from_u64(c.x), kcy = rt.key_tiled ? bits_fp(c.y) : fp_from_u64(c.y);
+            pr[(2 * v) * 256 + tid] = fp_mulmod(xd[2 * v], kax, f);
+            pr[(2 * v + 1) * 256 + tid] = fp_mulmod(xd[2 * v + 1], kay, f);
+            pr[(8 + 2 * v) * 256 + tid] = fp_mulmod(xd[2 * v], kcx, f);
+            pr[(8 + 2 * v + 1) * 256 + tid] = fp_mulmod(xd[2 * v + 1], kcy, f);
+        }
+        cl.sync();
+        if (i < 2) {
+            for (int kk = 0; kk < n_k; kk++) {
+                const int k = i + kk;
+                double s[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) s[e] = 0.0;
+                for (int r = 0; r < L; r++) {
+                    const double *rp = cl.map_shared_rank(pr, r) + k * 2048 + tid;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) s[e] = __dadd_rn(s[e], rp[e * 256]);
+                }
+                u64 *dst = ACC + (((u64)b * 2 + k) * (L + 1) + jj) * G::N + t0;
+                if (fuse_inv && jj == L) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) s[e] = fp_reduce(s[e], f);
+                    __syncthreads();   // own component-k block fully read: it becomes the exchange buffer
+                    inv_row_pass_fp<LOGN>(s, t.twid + (size_t)pj * G::N, f, t0, pr + k * 2048);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) dst[row_strided_li<LOGN>(e)] = fp_bits(s[e]);
+                } else {
+                    u64 r8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) r8[e] = fp_to_canonical(s[e], f);
+                    store8(dst + 8 * tid, r8);
+                }
+            }
+        }
+    } else {
+        u64 *plo = dsm, *phi = dsm + 4096;   // [2][8][256] each
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            ulonglong2 a = __ldg(k0 + kstep * v), c = __ldg(k1 + kstep * v);
+            plo[(2 * v) * 256 + tid] = x[2 * v] * a.x;
+            phi[(2 * v) * 256 + tid] = __umul64hi(x[2 * v], a.x);
+            plo[(2 * v + 1) * 256 + tid] = x[2 * v + 1] * a.y;
+            phi[(2 * v + 1) * 256 + tid] = __umul64hi(x[2 * v + 1], a.y);
+            plo[(8 + 2 * v) * 256 + tid] = x[2 * v] * c.x;
+            phi[(8 + 2 * v) * 256 + tid] = __umul64hi(x[2 * v], c.x);
+            plo[(8 + 2 * v + 1) * 256 + tid] = x[2 * v + 1] * c.y;
+            phi[(8 + 2 * v + 1) * 256 + tid] = __umul64hi(x[2 * v + 1], c.y);
+        }
+        cl.sync();
+        if (i < 2) {
+            for (int kk = 0; kk < n_k; kk++) {
+                const int k = i + kk;
+                u64 lo[8], hi[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) lo[e] = hi[e] = 0;
+                for (int r = 0; r < L; r++) {
+                    const u64 *rl = cl.map_shared_rank(plo, r) + k * 2048 + tid;
+                    const u64 *rh = cl.map_shared_rank(phi, r) + k * 2048 + tid;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const u64 al = rl[e * 256], ah = rh[e * 256];
+                        lo[e] += al;
+                        hi[e] += ah + (lo[e] < al);
+                    }
+                }
+                u64 r8[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) r8[e] = barrett128(lo[e], hi[e], m);
+                u64 *dst = ACC + (((u64)b * 2 + k) * (L + 1) + jj) * G::N + t0;
+                if (fuse_inv && jj == L) {
+                    __syncthreads();   // own component-k block fully read: it becomes the exchange buffer
+                    inv_row_pass<LOGN>(r8, t.twi + (size_t)pj * G::N, m, t0, plo + k * 2048);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) dst[row_strided_li<LOGN>(e)] = r8[e];
+                } else {
+                    store8(dst + 8 * tid, r8);
+                }
+            }
+        }
+    }
+    cl.sync();   // peers may still be reading this CTA's products
 }
 
 // (7) mod-down / rescale, column pass: R holds r' = (INTT(last limb) + half) mod q_a for poly

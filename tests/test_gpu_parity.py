@@ -53,6 +53,22 @@ def test_ntt_limb_per_cta_variant_bit_exact():
     assert res.returncode == 0 and "passed" in res.stdout, res.stdout[-2000:]
 
 
+def test_cluster_inner_product_variant_bit_exact():
+    """the thread-block-cluster inner product (k_ks_mac_cl: one CTA per digit, partial products summed through distributed
+    shared memory; default only for single ciphertexts at N <= 16384) forced for every batch size and degree
+    (CKKS_CLUSTER_BELOW=1000): the key-switch parity tests re-run in a child process must still match the oracle bit for bit"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CKKS_CLUSTER_BELOW="1000")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                          "-k", "test_relinearize_bit_exact or test_apply_galois_bit_exact or test_rotate_vector_naf_chain or "
+                                "test_rotate_sum_chain_matches_sequential or test_extreme_modulus_chains or test_random_mixed_chains"],
+                         env=env, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert res.returncode == 0 and "passed" in res.stdout, res.stdout[-2000:]
+
+
 def test_ntt_bfv_default_primes(po, eng):
     """config 2 chains: SEAL's BFVDefault primes for N = 4096 / 8192 (benchmark.cpp:137)"""
     import torch
