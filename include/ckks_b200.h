@@ -168,6 +168,10 @@ typedef struct ckks_rotplan ckks_rotplan;
 int ckks_rotplan_create(ckks_ctx *ctx, ckks_keyset *ks, const int *steps, int batch, ckks_rotplan **out);
 void ckks_rotplan_destroy(ckks_rotplan *plan);
 uint64_t ckks_rotplan_keyswitches(const ckks_rotplan *plan); /* total Galois key switches per run */
+/* key switches per run when every entry rotates the same input ciphertext (ckks_rotate_plan with in->batch == 1): rotations
+ * whose NAF chains begin with the same terms share those key switches; every output is still bit-identical to its own
+ * rotate_vector call (Evaluator::rotate_vector, helper.h:252-257) */
+uint64_t ckks_rotplan_keyswitches_shared(const ckks_rotplan *plan);
 int ckks_rotplan_rounds(const ckks_rotplan *plan);
 /* in->batch is the plan's batch, or 1 to rotate one ciphertext by every step of the plan;
  * out and scratch (needed when some entry has more than one NAF term) are plan-batch views */

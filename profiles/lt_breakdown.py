@@ -28,7 +28,7 @@ U, v = rng.uniform(0, 1, (d, d)), rng.uniform(0, 1, d)
 ct = encr.encrypt(enc.encode(v, SCALE))
 diags = enc.encode(wl.all_diagonals(U), SCALE)
 plans = wl.PlanCache(ctx, keys)
-mine = par.shard_units_weighted([par.naf_weight(l) for l in range(d)], 0, world)
+mine = par.shard_rotations_shared(list(range(d)), 0, world)
 plan = plans.get(mine)
 dl = eng.Ciphertext(ctx, diags.data[torch.tensor(mine, device=ctx.device)].contiguous(), diags.limbs, diags.scale)
 
@@ -58,7 +58,7 @@ graph = torch.cuda.CUDAGraph()
 with torch.cuda.graph(graph):
     out = ev.multiply_plain_sum(ev.rotate_plan(wl.duplicate_fill(ev, ct, d, keys), plan), dl)
 t_graph, _ = timed(graph.replay)
-print("rank 0 of %d: %d diagonals, %d key switches in %d rounds (round sizes via plan)" % (world, len(mine), plan.keyswitches, plan.rounds))
+print("rank 0 of %d: %d diagonals, %d key switches in %d rounds (round sizes via plan)" % (world, len(mine), plan.keyswitches_shared, plan.rounds))
 print("duplicate_fill (1 key switch + add) %.1f us | rotate_plan %.1f us | multiply_plain_sum %.1f us | add_many over %d partials %.1f us" % (
     t_dup, t_rot, t_mps, world, t_add))
 print("local part end to end: eager %.1f us, one replayed CUDA graph %.1f us" % (t_all, t_graph))

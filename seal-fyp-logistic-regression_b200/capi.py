@@ -81,6 +81,7 @@ SIGNATURES = {
     "ckks_rotplan_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_int, _vpp]),
     "ckks_rotplan_destroy": (None, [C.c_void_p]),
     "ckks_rotplan_keyswitches": (C.c_uint64, [C.c_void_p]),
+    "ckks_rotplan_keyswitches_shared": (C.c_uint64, [C.c_void_p]),
     "ckks_rotplan_rounds": (C.c_int, [C.c_void_p]),
     "ckks_rotate_plan": (C.c_int, [C.c_void_p, C.c_void_p, _VP, _VP, _VP, C.c_void_p]),
     "ckks_rotate_plan_hoisted": (C.c_int, [C.c_void_p, C.c_void_p, _VP, _VP, C.c_void_p]),

@@ -153,6 +153,15 @@ struct ckks_rotplan {
     std::vector<int> zero_entries;
     KsSel *d_sel = nullptr;
     uint64_t keyswitches = 0;
+    // shared-prefix form, used when every entry rotates the SAME input ciphertext (in->batch == 1): rotations whose NAF
+    // chains start with the same terms share those key switches -- the intermediate ciphertext is a deterministic function
+    // of the input and the keys, so every output stays bit-identical to its own rotate_vector call (helper.h:252-257:
+    // d = 128 needs 169 instead of 355 key switches).  Node storage: the output entry of the rotation that ends at the
+    // node, else a scratch entry.
+    std::vector<int> sh_round_off, sh_round_cnt;
+    std::vector<std::pair<int, int>> sh_copies;   // (from entry, to entry) for repeated steps
+    KsSel *d_sel_sh = nullptr;
+    uint64_t keyswitches_shared = 0;
 };
 
 static int upload_vec(void **dst, const void *src, size_t bytes) {
@@ -1132,18 +1141,72 @@ extern "C" int ckks_rotplan_create(ckks_ctx *c, ckks_keyset *ks, const int *step
             const int m = (int)terms[b].size();
             if ((size_t)m <= r) continue;
             KsSel e;
-            e.entry = b;
+            e.entry = e.sentry = b;
             e.slot = ks->slot_of.at(ckks::galois_elt_from_step(c->log_n, terms[b][r]));
-            e.src = r == 0 ? 0 : (((m - (int)r) % 2 == 0) ? 1 : 2);
-            e.dst = ((m - 1 - (int)r) % 2 == 0) ? 1 : 2;
+            e.src = (short)(r == 0 ? 0 : (((m - (int)r) % 2 == 0) ? 1 : 2));
+            e.dst = (short)(((m - 1 - (int)r) % 2 == 0) ? 1 : 2);
             sel.push_back(e);
         }
         p->round_cnt.push_back((int)sel.size() - p->round_off.back());
     }
+    // shared-prefix form: a trie over the NAF term sequences
+    struct Node {
+        int parent, term, depth, view, entry;
+        std::map<int, int> kids;
+    };
+    std::vector<Node> nodes(1, Node{-1, 0, 0, 0, 0, {}});
+    std::vector<KsSel> sh;
+    int next_tmp = 0;
+    bool shared_ok = batch > 1 && rounds > 1;
+    for (int b = 0; b < batch && shared_ok; b++) {
+        int cur = 0;
+        for (size_t r = 0; r < terms[b].size(); r++) {
+            auto it = nodes[cur].kids.find(terms[b][r]);
+            if (it == nodes[cur].kids.end()) {
+                nodes.push_back(Node{cur, terms[b][r], (int)r + 1, -1, -1, {}});
+                nodes[cur].kids[terms[b][r]] = (int)nodes.size() - 1;
+                cur = (int)nodes.size() - 1;
+            } else {
+                cur = it->second;
+            }
+        }
+        if (cur == 0) continue;                       // rotate by 0: copied from the input
+        if (nodes[cur].view == 1) p->sh_copies.push_back({nodes[cur].entry, b});   // the same step twice
+        else nodes[cur].view = 1, nodes[cur].entry = b;
+    }
+    for (size_t q = 1; q < nodes.size() && shared_ok; q++)
+        if (nodes[q].view < 0) {
+            nodes[q].view = 2;
+            nodes[q].entry = next_tmp++;
+            if (next_tmp > batch) shared_ok = false;  // more pure intermediates than scratch entries: keep the plain form
+        }
+    if (shared_ok && nodes.size() - 1 < p->keyswitches) {
+        for (size_t r = 1; r <= rounds; r++) {
+            p->sh_round_off.push_back((int)sh.size());
+            for (size_t q = 1; q < nodes.size(); q++) {
+                if ((size_t)nodes[q].depth != r) continue;
+                const Node &par = nodes[nodes[q].parent];
+                KsSel e;
+                e.entry = nodes[q].entry;
+                e.slot = ks->slot_of.at(ckks::galois_elt_from_step(c->log_n, nodes[q].term));
+                e.src = (short)(nodes[q].parent == 0 ? 0 : par.view);
+                e.dst = (short)nodes[q].view;
+                e.sentry = nodes[q].parent == 0 ? 0 : par.entry;
+                sh.push_back(e);
+            }
+            p->sh_round_cnt.push_back((int)sh.size() - p->sh_round_off.back());
+        }
+        p->keyswitches_shared = sh.size();
+    } else {
+        p->sh_copies.clear();
+        p->keyswitches_shared = p->keyswitches;
+    }
     if (!sel.empty()) {
         if (cudaSetDevice(c->device) != cudaSuccess || cudaMalloc((void **)&p->d_sel, sel.size() * sizeof(KsSel)) != cudaSuccess ||
-            cudaMemcpy(p->d_sel, sel.data(), sel.size() * sizeof(KsSel), cudaMemcpyHostToDevice) != cudaSuccess) {
-            delete p;
+            cudaMemcpy(p->d_sel, sel.data(), sel.size() * sizeof(KsSel), cudaMemcpyHostToDevice) != cudaSuccess ||
+            (!sh.empty() && (cudaMalloc((void **)&p->d_sel_sh, sh.size() * sizeof(KsSel)) != cudaSuccess ||
+                             cudaMemcpy(p->d_sel_sh, sh.data(), sh.size() * sizeof(KsSel), cudaMemcpyHostToDevice) != cudaSuccess))) {
+            ckks_rotplan_destroy(p);
             return fail(CKKS_ERR_CUDA, "rotplan: device allocation failed");
         }
     }
@@ -1153,9 +1216,11 @@ extern "C" int ckks_rotplan_create(ckks_ctx *c, ckks_keyset *ks, const int *step
 extern "C" void ckks_rotplan_destroy(ckks_rotplan *p) {
     if (!p) return;
     cudaFree(p->d_sel);
+    cudaFree(p->d_sel_sh);
     delete p;
 }
 extern "C" uint64_t ckks_rotplan_keyswitches(const ckks_rotplan *p) { return p->keyswitches; }
+extern "C" uint64_t ckks_rotplan_keyswitches_shared(const ckks_rotplan *p) { return p->keyswitches_shared; }
 extern "C" int ckks_rotplan_rounds(const ckks_rotplan *p) { return (int)p->round_cnt.size(); }
 
 extern "C" int ckks_rotate_plan(ckks_ctx *c, const ckks_rotplan *p, const ckks_view *in, const ckks_view *out,
@@ -1192,6 +1257,21 @@ extern "C" int ckks_rotate_plan(ckks_ctx *c, const ckks_rotplan *p, const ckks_v
         dst.data += (u64)b * dst.bs;
         k_ew_copy<<<ew_grid(c, 2 * in->limbs, 1), 256, 0, st>>>(src, dst, in->limbs, c->n);
         LAUNCH_CHECK(c);
+    }
+    static const bool share = !(getenv("CKKS_ROT_SHARE") && atoi(getenv("CKKS_ROT_SHARE")) == 0);
+    if (share && in->batch == 1 && p->d_sel_sh) {   // one input ciphertext: rotations share their common NAF prefixes
+        for (size_t r = 0; r < p->sh_round_cnt.size(); r++) {
+            rt.sel = p->d_sel_sh + p->sh_round_off[r];
+            if ((rc = keyswitch_lanes(c, 2, in->limbs, p->sh_round_cnt[r], rt, st))) return rc;
+        }
+        for (const auto &cp : p->sh_copies) {
+            DView src = rt.v[1], dst = rt.v[1];
+            src.data += (u64)cp.first * src.bs;
+            dst.data += (u64)cp.second * dst.bs;
+            k_ew_copy<<<ew_grid(c, 2 * in->limbs, 1), 256, 0, st>>>(src, dst, in->limbs, c->n);
+            LAUNCH_CHECK(c);
+        }
+        return CKKS_OK;
     }
     for (size_t r = 0; r < p->round_cnt.size(); r++) {
         rt.sel = p->d_sel + p->round_off[r];

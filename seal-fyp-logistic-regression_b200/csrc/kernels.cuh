@@ -100,10 +100,11 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // it reads from and writes to.  With sel == nullptr slot z works on entry z with key 0,
 // reading view 0 and writing view 1.
 struct KsSel {
-    int entry;
-    int slot;
-    int src;
-    int dst;
+    int entry;    // batch entry written (view dst)
+    int slot;     // key slot
+    short src;    // view read
+    short dst;    // view written
+    int sentry;   // batch entry read (view src); differs from `entry` only in shared-prefix rotation plans
 };
 struct KsRoute {
     DView v[3];                        // in, out, scratch
@@ -121,7 +122,7 @@ struct KsRoute {
 __device__ __forceinline__ KsSel route_sel(const KsRoute &r, int z) {
     if (r.sel) return r.sel[r.b0 + z];
     KsSel s;
-    s.entry = r.b0 + z; s.slot = 0; s.src = 0; s.dst = 1;
+    s.entry = s.sentry = r.b0 + z; s.slot = 0; s.src = 0; s.dst = 1;
     return s;
 }
 __device__ __forceinline__ const uint32_t *route_perm(const KsRoute &r, const KsSel &s) {
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(NTT_THREADS, V_OCC_INTT) k_ks_intt_row(KsRoute
     const KsSel sl = route_sel(rt, b);
     const DView tgt = rt.v[sl.src];
     const uint32_t *__restrict__ perm = GALOIS ? route_perm(rt, sl) : nullptr;
-    const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
+    const u64 *in = tgt.data + sl.sentry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
     u64 *out = D + ((u64)b * L + i) * G::N;
     const ModConst m = load_mod(t, i);
     const int t0 = blockIdx.x * NTT_TILE;
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ks_mac(const u64 *T1, KsRout
         prefetch_l2(ksk + (((u64)i * 2 + 0) * K + pj) * G::N + t0 + 8 * threadIdx.x);
         prefetch_l2(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
         if (i == pj) {
-            const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
+            const u64 *in = tgt.data + sl.sentry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
             if (GALOIS) {
                 unsigned ix[8];
                 load_perm8(ix, perm + t0 + 8 * threadIdx.x);
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(NTT_THREADS, V_MACFP_OCC) k_ks_mac_fp(const u6
         prefetch_l2(ksk + (((u64)i * 2 + 1) * K + pj) * G::N + t0 + 8 * threadIdx.x);
 #endif
         if (i == pj) {
-            const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
+            const u64 *in = tgt.data + sl.sentry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
             u64 xi[8];
             if (GALOIS) {
                 unsigned ix[8];
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ks_mac_cl(const u64 *T1, KsR
     u64 x[8];
     double xd[8];
     if (i == pj) {   // the digit's own prime: the NTT-form limb of the target itself
-        const u64 *in = tgt.data + sl.entry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
+        const u64 *in = tgt.data + sl.sentry * tgt.bs + rt.tgt_poly * tgt.ps + (u64)i * G::N;
         if (GALOIS) {
             unsigned ix[8];
             load_perm8(ix, perm + t0 + 8 * tid);
@@ -1081,12 +1082,12 @@ __global__ void __launch_bounds__(NTT_THREADS, V_MDROW_OCC) k_md_fwd_row(const u
         load8(mv, mi);
 #endif
         if (MODE == 1) {
-            load8(bv, base.data + sl.entry * base.bs + s * base.ps + (u64)j * G::N + t0 + 8 * threadIdx.x);
+            load8(bv, base.data + sl.sentry * base.bs + s * base.ps + (u64)j * G::N + t0 + 8 * threadIdx.x);
         } else if (MODE == 2) {
             if (s == 0) {
                 unsigned ix[8];
                 load_perm8(ix, perm + t0 + 8 * threadIdx.x);
-                const u64 *bp = base.data + sl.entry * base.bs + (u64)j * G::N;
+                const u64 *bp = base.data + sl.sentry * base.bs + (u64)j * G::N;
 #pragma unroll
                 for (int e = 0; e < 8; e++) bv[e] = bp[ix[e]];
             }

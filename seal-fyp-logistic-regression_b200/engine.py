@@ -531,6 +531,8 @@ class RotPlan:
         check(ctx.lib.ckks_rotplan_create(ctx._h, keys._h, arr, self.batch, C.byref(h)))
         self._h = h
         self.keyswitches = int(ctx.lib.ckks_rotplan_keyswitches(h))
+        # with ONE input ciphertext the rotations share common NAF prefixes (bit-identical outputs, fewer key switches)
+        self.keyswitches_shared = int(ctx.lib.ckks_rotplan_keyswitches_shared(h))
         self.rounds = int(ctx.lib.ckks_rotplan_rounds(h))
 
     def __del__(self):

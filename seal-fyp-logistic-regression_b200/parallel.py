@@ -53,6 +53,64 @@ def shard_units_weighted(weights, rank, world_size):
     return sorted(mine)
 
 
+def naf_terms(steps):
+    """the signed power-of-two terms SEAL's rotate_vector applies for `steps`, in its order (least significant
+    first; util::naf, SURVEY.md A.6)"""
+    v, i, out = abs(int(steps)), 0, []
+    sign = 1 if steps >= 0 else -1
+    while v:
+        if v & 1:
+            z = 2 - (v & 3)
+            v -= z
+            out.append(sign * z * (1 << i))
+        v >>= 1
+        i += 1
+    return out
+
+
+def shard_rotations_shared(steps, rank, world_size):
+    """partition the rotations of ONE ciphertext for rotation plans that share common NAF prefixes
+    (ckks_rotplan_keyswitches_shared): rotations are ordered by their term sequences, so that rotations with a common
+    prefix are neighbours, and the order is cut into world_size contiguous runs of equal cost, where a rotation costs the
+    terms it does not share with its predecessor in the run (= the key switches the run's prefix tree adds for it).
+    d = 128: 169 key switches on 1 GPU, 85 / 85 on 2, 4 x 43 on 4, 8 x 22 on 8 (cost-balanced without regard to prefixes: 90 / 51 / 31).
+    Returns this rank's indices into `steps`, increasing."""
+    seqs = [tuple(naf_terms(st)) for st in steps]
+    order = sorted(range(len(steps)), key=lambda u: (seqs[u], u))
+
+    def lcp(a, b):
+        n = 0
+        while n < len(a) and n < len(b) and a[n] == b[n]:
+            n += 1
+        return n
+
+    def cuts(limit):
+        """greedy: fewest runs with cost <= limit each; returns the list of runs"""
+        runs, cur, cost = [], [], 0
+        for u in order:
+            add = len(seqs[u]) - (lcp(seqs[cur[-1]], seqs[u]) if cur else 0)
+            if cur and cost + add > limit:
+                runs.append(cur)
+                cur, cost = [], 0
+                add = len(seqs[u])
+            cur.append(u)
+            cost += add
+        if cur:
+            runs.append(cur)
+        return runs
+
+    lo, hi = max([len(q) for q in seqs] + [1]), sum(len(q) for q in seqs) + 1
+    while lo < hi:                       # smallest per-run cost that needs at most world_size runs
+        mid = (lo + hi) // 2
+        if len(cuts(mid)) <= world_size:
+            hi = mid
+        else:
+            lo = mid + 1
+    runs = cuts(lo)
+    runs += [[] for _ in range(world_size - len(runs))]
+    return sorted(runs[rank])
+
+
 def gather_partials(t):
     """all-gather one tensor per rank -> [G, ...] on every rank (any backend)"""
     rank, G = world()

@@ -91,6 +91,36 @@ def test_weighted_shards_balance_naf_cost():
             assert all(p == sorted(p) for p in parts)
 
 
+def test_prefix_aware_shards_for_shared_rotation_plans():
+    """rotations of one ciphertext share their common NAF prefixes (ckks_rotplan_keyswitches_shared): the sharding keeps
+    rotations with a common prefix on one rank and balances the resulting prefix-tree sizes"""
+    par = importlib.import_module(PKG + ".parallel")
+    from oracle import pyoracle as po
+
+    def tree(steps):
+        nodes = set()
+        for st in steps:
+            t = par.naf_terms(st)
+            nodes.update(tuple(t[:k]) for k in range(1, len(t) + 1))
+        return len(nodes)
+
+    for l in list(range(-130, 130)) + [4095, -8192]:
+        assert par.naf_terms(l) == list(po.naf(l)), l
+    assert tree(range(128)) == 169 and sum(par.naf_weight(l) for l in range(128)) == 355
+    for d, want in ((64, {1: 84, 2: 43, 4: 22, 8: 12}), (128, {1: 169, 2: 85, 4: 43, 8: 22})):
+        w = [par.naf_weight(l) for l in range(d)]
+        for G in (1, 2, 4, 8):
+            parts = [par.shard_rotations_shared(list(range(d)), r, G) for r in range(G)]
+            assert sorted(sum(parts, [])) == list(range(d))
+            assert all(p == sorted(p) for p in parts)
+            assert max(tree(p) for p in parts) == want[G], (d, G, [tree(p) for p in parts])
+            # never worse than the cost-balanced split that ignores prefixes
+            assert max(tree(p) for p in parts) <= max(tree(par.shard_units_weighted(w, r, G)) for r in range(G))
+    # arbitrary step lists, more ranks than rotations
+    parts = [par.shard_rotations_shared([5, -3, 21], r, 4) for r in range(4)]
+    assert sorted(sum(parts, [])) == [0, 1, 2]
+
+
 def test_strong_scaling_units_partition_the_problem():
     """bench.py --scaling strong: the 32 (mini-batch, feature) gradient chains of one 8 x 32768 problem"""
     import importlib.util

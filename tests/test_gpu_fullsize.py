@@ -29,6 +29,7 @@ def test_config3_linear_transform_n16384(make_fixture, d):
     want = rw.linear_transform_plain(E, rw.OCt(ct, scale), [rw.OCt(p, scale) for p in pts])
     got = wl.linear_transform_plain(fx.ev, fx.ctx.upload(ct, scale=scale), fx.ctx.upload_plain(pts, scale=scale), fx.keys, plans)
     assert plans.get(range(d)).keyswitches + len(__import__("oracle.pyoracle", fromlist=["naf"]).naf(-d)) == {64: 157, 128: 356}[d]
+    assert plans.get(range(d)).keyswitches_shared == {64: 84, 128: 169}[d]    # what actually runs: common NAF prefixes once
     assert np.array_equal(got.numpy()[0], want.data)
     dec = fx.orc.decode(fx.orc.decrypt(fx.sk, got.numpy()[0]), got.scale)[:d]
     assert np.abs(dec - U @ v).max() < 1e-3

@@ -164,6 +164,40 @@ def test_rotate_vector_naf_chain(make_fixture):
         fx.ev.rotate_vector(d, fx.n // 2, fx.keys)   # "step count too large"
 
 
+def test_rotation_plan_shares_naf_prefixes_bit_exact(make_fixture, eng):
+    """a rotation plan applied to ONE ciphertext runs the common leading NAF terms of its rotations once
+    (ckks_rotplan_keyswitches_shared): every output must still equal the oracle's own rotate_vector of that step, bit for
+    bit -- including a step that is a proper prefix of another (5 = [1,4] and 21 = [1,4,16]), repeated steps, step 0, a
+    level below the top, and a plan whose pure intermediates outnumber its entries (kept in the plain form)"""
+    fx = make_fixture(12, CHAINS[12], steps=(1, -1, 2, -2, 4, -4, 8, -8, 16, -16, 32, 64))
+    rng = np.random.default_rng(29)
+    steps = [5, 21, 85, 3, 0, 5, -3, 13, 19, 11, 27, 7, 1, 64, 43, 21]
+    plan = eng.RotPlan(fx.ctx, fx.keys, steps)
+    assert plan.keyswitches_shared < plan.keyswitches
+    for L in (fx.L, fx.L - 1):
+        a = fx.random_ct(rng, 1, 2, L)
+        d = fx.ctx.upload(a)
+        got = fx.ev.rotate_plan(d, plan).numpy()
+        for i, st in enumerate(steps):
+            assert np.array_equal(got[i], fx.orc.rotate(a[0], st, fx.gks)), (L, st)
+    # distinct inputs per entry: nothing to share, same plan object
+    a = fx.random_ct(rng, len(steps), 2, fx.L)
+    got = fx.ev.rotate_plan(fx.ctx.upload(a), plan).numpy()
+    for i, st in enumerate(steps):
+        assert np.array_equal(got[i], fx.orc.rotate(a[i], st, fx.gks)), st
+    # two entries, four pure intermediates (85 = [1, 4, 16, 64], 81 = [1, 16, 64] share only [1]): more than the scratch holds
+    deep = eng.RotPlan(fx.ctx, fx.keys, [85, 81])
+    assert deep.keyswitches_shared == deep.keyswitches == 7
+    a = fx.random_ct(rng, 1, 2, fx.L)
+    got = fx.ev.rotate_plan(fx.ctx.upload(a), deep).numpy()
+    assert np.array_equal(got[0], fx.orc.rotate(a[0], 85, fx.gks)) and np.array_equal(got[1], fx.orc.rotate(a[0], 81, fx.gks))
+    # 85 and 21 = [1, 4, 16]: one chain, the shorter rotation is an inner node of the longer one
+    chain = eng.RotPlan(fx.ctx, fx.keys, [85, 21])
+    assert chain.keyswitches_shared == 4 and chain.keyswitches == 7
+    got = fx.ev.rotate_plan(fx.ctx.upload(a), chain).numpy()
+    assert np.array_equal(got[0], fx.orc.rotate(a[0], 85, fx.gks)) and np.array_equal(got[1], fx.orc.rotate(a[0], 21, fx.gks))
+
+
 @pytest.mark.parametrize("log_n", [12, 13, 14, 15])
 def test_rescale_bit_exact(make_fixture, log_n):
     fx = make_fixture(log_n, CHAINS[log_n])
