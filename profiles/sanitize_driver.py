@@ -38,7 +38,9 @@ for log_n in [int(a) for a in sys.argv[1:]] or [12, 13]:
     rot = ev.rotate_vector(ct, 3, keys)                          # NAF rounds (1 + 2)
     plan = eng.RotPlan(ctx, keys, [1, 2, 3, -1, 5])
     one = ct[0:1]
-    r1 = ev.rotate_plan(one, plan)                               # batched plan
+    r0 = ev.rotate_vector(one, 5, keys)                          # single ciphertext: thread-block-cluster inner product
+    q0 = ev.relinearize(ev.multiply(one, one), keys)
+    r1 = ev.rotate_plan(one, plan)                               # batched plan, shared NAF prefixes
     hplan = eng.RotPlan(ctx, keys, [1, 2, 4, -1])
     r2 = ev.rotate_plan_hoisted(one, hplan)                      # hoisted kernels
     dup, acc = ct.clone(), ct.clone()
