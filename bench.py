@@ -517,6 +517,7 @@ def run_gpu(args):
                               "frac": epoch_alg / (ms / args.steps * 1e-3) / 1e9 / peak,
                               "keyswitches_per_step_per_gpu": prob.n_units * B_MINI},
         "pipe_utilisation": prof.get("pipe_utilisation"),
+        "arithmetic_ceiling": arithmetic_ceiling(Lk, ks_ms * 1e3 / nb),
         "note": "HBM is the roofline north_star names; the key switch does L^2+3L+2 = 20 size-N NTTs per 9.4 MB, so issue "
                 "slots and the integer-multiplier / FP64 pipes bind before HBM (DESIGN.md section 4; pipe_utilisation = ncu "
                 "sm__inst_executed_pipe_* of the same launch group, profiles/)",
@@ -713,6 +714,25 @@ def linear_transform_sharded(torch, eng, client, par, local, rank, world, timed,
                     "bit-identical to its own rotate_vector call",
             "cuda_graph": graphed, "ms_eager_launches": ms_eager / 20, "rounds": int(plans.get(mine).rounds),
             "bit_identical_to_unsharded": same, "max_abs_err_vs_plain": err, "bsgs_mode": bsgs, "hoisted_mode": hoisted}
+
+
+def arithmetic_ceiling(L, us_per_key_switch):
+    """the key switch against the measured throughput of its own butterflies (profiles/micro/butterfly_rates.cu: the
+    engine's radix-8 register steps on register-resident data, no memory traffic): time the 20 (L = 3) transforms'
+    butterflies alone would take on this GPU, and the share of the live-timed key switch that is"""
+    path = os.path.join(ROOT, "profiles", "butterfly_rates.json")
+    if not os.path.exists(path):
+        return None
+    doc = json.load(open(path))
+    key = "key_switch_N32768_L%d" % L
+    if key not in doc:
+        return None
+    serial = doc[key]["us_butterflies_only_pipes_serial"]
+    mixed = doc[key].get("us_butterflies_only_measured_concurrent_mix", serial)
+    return {"us_per_key_switch_butterflies_only": mixed, "us_per_key_switch_measured": us_per_key_switch,
+            "frac": mixed / us_per_key_switch, "transforms": doc[key]["transforms"], "source": doc["source"],
+            "note": "compute ceiling of the butterflies alone (integer and FP64 kernels running concurrently); the inner "
+                    "product, reductions, exchanges and memory instructions come on top"}
 
 
 def _primes():
