@@ -116,7 +116,8 @@ int main() {
     }
     // both kinds at once (two streams, equal butterfly counts -- the 10 : 10 mix of L = 3), CTAs of both kernels co-resident
     {
-        const int iters = 2048, blocks = 148 * 8, threads = 256;
+        // 2 + 2 CTAs per SM: one wave of each kernel, co-resident (a full grid of either kernel would fill the register file)
+        const int iters = 8192, blocks = 148 * 2, threads = 256;
         cudaStream_t s0, s1;
         cudaStreamCreate(&s0);
         cudaStreamCreate(&s1);
@@ -138,6 +139,19 @@ int main() {
         float ms;
         cudaEventElapsedTime(&ms, e0, e1);
         const double bf = 2.0 * blocks * threads * 12.0 * iters;
+        // the same two launches one after the other, for the comparison
+        cudaEvent_t f0, f1;
+        cudaEventCreate(&f0);
+        cudaEventCreate(&f1);
+        cudaDeviceSynchronize();
+        cudaEventRecord(f0, s0);
+        k_bfly<0, 4><<<blocks, threads, 0, s0>>>(out, m, f, 12345, iters);
+        k_bfly<2, 4><<<blocks, threads, 0, s0>>>(out2, m, f, 12345, iters);
+        cudaEventRecord(f1, s0);
+        cudaEventSynchronize(f1);
+        float ms_serial;
+        cudaEventElapsedTime(&ms_serial, f0, f1);
+        printf("2 + 2 CTAs per SM: concurrent %.3f ms, back to back %.3f ms\n", ms, ms_serial);
         printf("integer forward + FP64 forward concurrently (two streams): %.1f G butterflies/s -> %.2f us per key switch of 20 x 245760 "
                "butterflies\n", bf / (ms * 1e-3) / 1e9, 20 * 245760.0 / (bf / (ms * 1e-3)) * 1e6);
     }
