@@ -11,6 +11,34 @@
 #include "modarith.cuh"
 #include "ntt_passes.cuh"
 
+// experiment: truncated Shoup product whose two cross terms hi32(s1*x0) + hi32(s0*x1) come from the FP64 pipe
+// (round-toward-zero products: never above the true value, at most 1 below), leaving 3 wide + 4 low multiplies
+__device__ __forceinline__ double u32_to_double(unsigned v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+__device__ __forceinline__ u64 shoup_lazy_v2(u64 x, u64 w, u64 ws, u64 negp) {
+    const unsigned x0 = (unsigned)x, x1 = (unsigned)(x >> 32);
+    const unsigned s0 = (unsigned)ws, s1 = (unsigned)(ws >> 32);
+    const double mid = __fma_rz(u32_to_double(x0), u32_to_double(s1), __dmul_rz(u32_to_double(x1), u32_to_double(s0)));
+    const u64 tb = (u64)__double_as_longlong(__fma_rz(mid, 0x1p-32, 4503599627370496.0));
+    const u64 q = (u64)x1 * s1 + (tb & 0x3ffffffffull);
+    return w * x + q * negp;
+}
+__device__ __forceinline__ void ct_bfly_v2(u64 &X, u64 &Y, u64 w, u64 ws, const ModConst &m) {
+    u64 x = lazy_sub(X, m.p4, (unsigned)m.p4hi);
+    u64 t = shoup_lazy_v2(Y, w, ws, m.negp);
+    X = x + t;
+    Y = x + m.p4 - t;
+}
+__device__ __forceinline__ void fwd8_v2(u64 (&x)[8], const Tw8 &t, const ModConst &m) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) ct_bfly_v2(x[e], x[e + 4], t.w[0].x, t.w[0].y, m);
+    ct_bfly_v2(x[0], x[2], t.w[1].x, t.w[1].y, m);
+    ct_bfly_v2(x[1], x[3], t.w[1].x, t.w[1].y, m);
+    ct_bfly_v2(x[4], x[6], t.w[2].x, t.w[2].y, m);
+    ct_bfly_v2(x[5], x[7], t.w[2].x, t.w[2].y, m);
+#pragma unroll
+    for (int q = 0; q < 4; q++) ct_bfly_v2(x[2 * q], x[2 * q + 1], t.w[3 + q].x, t.w[3 + q].y, m);
+}
+
 template <int MODE, int OCC>
 __global__ void __launch_bounds__(256, OCC) k_bfly(u64 *out, ModConst m, FpConst f, u64 seed, int iters) {
     u64 x[8];
@@ -34,6 +62,7 @@ __global__ void __launch_bounds__(256, OCC) k_bfly(u64 *out, ModConst m, FpConst
         if (MODE == 1) inv8<0>(x, t, m);                     // 12 integer Gentleman-Sande butterflies
         if (MODE == 2) fwd8d<0>(xd, td, f);                  // 12 FP64 butterflies (lazy: reduce as the passes do)
         if (MODE == 3) inv8d<0>(xd, td, f);
+        if (MODE == 4) fwd8_v2(x, t, m);                     // experiment: cross terms of the Shoup quotient on the FP64 pipe
         if (MODE == 2 || MODE == 3) {
             if ((it & 3) == 3) {
 #pragma unroll
@@ -106,6 +135,8 @@ int main() {
     r[5] = run<2, 8>("FP64 forward (fwd8d, 40-bit)", out, m, f);
     r[6] = run<3, 4>("FP64 inverse (inv8d, 40-bit)", out, m, f);
     r[7] = run<3, 8>("FP64 inverse (inv8d, 40-bit)", out, m, f);
+    run<4, 4>("integer forward, FP64 cross terms", out, m, f);
+    run<4, 8>("integer forward, FP64 cross terms", out, m, f);
     // one Galois key switch at N = 32768, L = 3, chain {60, 40, 40, ..., 60}: 20 transforms of 245760 butterflies --
     // integer: 4 forward into P/q0 of the mod-up + ... see DESIGN.md section 4: 7 forward + 3 inverse integer, 8 forward + 2 inverse FP64
     const double bi_f = 7 * 245760.0, bi_i = 3 * 245760.0, bf_f = 8 * 245760.0, bf_i = 2 * 245760.0;
