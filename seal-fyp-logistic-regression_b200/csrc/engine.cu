@@ -65,11 +65,13 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t 
 // thread-block-cluster launch (cluster = grid.x CTAs: the digits of one output tile), dynamic shared memory opted in once
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, size_t smem, cudaStream_t st, Args... args) {
-    static thread_local std::map<const void *, bool> ready;
-    if (!ready[(const void *)kernel]) {
+    static thread_local std::map<std::pair<int, const void *>, bool> ready;   // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!ready[{dev, (const void *)kernel}]) {
         cudaError_t e = cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        ready[(const void *)kernel] = true;
+        ready[{dev, (const void *)kernel}] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
