@@ -976,7 +976,13 @@ extern "C" int ckks_rotate_sum_chain(ckks_ctx *c, const ckks_keyset *ks, const c
         // one lane (special-prime INTT: 1-2 waves) overlap the long ones of the other.  Each lane replays a
         // cached CUDA graph of ping-pong steps; the lanes only meet again at the end of the chain.
         int nl = c->chain_lanes;
-        while (nl > 1 && B / nl < 8) nl--;
+        static const int lane_min = getenv("CKKS_LANE_MIN") ? atoi(getenv("CKKS_LANE_MIN")) : 0;   // ciphertexts per lane (0 = rule below)
+        while (nl > 1 && B / nl < (lane_min > 0 ? lane_min : 8)) nl--;
+        // small batches (the strong-scaling regime: 4 / 8 chains per GPU): lanes of TWO ciphertexts -- each lane's launches then
+        // take the split special-prime inner product and the lanes fill the GPU side by side.  Measured per chain step at
+        // N = 32768, L = 3: batch 4: 58.9 us (2 x 2) against 63.6 (one lane) and 62.3 (4 x 1); batch 8: 86.6 us (4 x 2) against
+        // 92.6 (one lane) and 95.9 (2 x 4); batch 16: 133.8 (2 x 8) against 137.5 (4 x 4); batch 2: one lane.
+        if (lane_min == 0 && c->chain_lanes >= 2 && B >= 4 && B <= 8 && B % 2 == 0) nl = B / 2;
         int split[5];
         for (int li = 0; li <= nl; li++) split[li] = (int)((long)B * li / nl);
         if (!c->ev_in) {
